@@ -1,0 +1,8 @@
+"""diffqcqp_b200 -- B200 (sm_100a) batched differentiable ADMM QP/QCQP solver.
+
+Drop-in for the QPFn2 / QCQPFn2 hot path of quentinll/diffqcqp (qcqp.py); see DESIGN.md.
+"""
+from .qcqp import QPFn2, QCQPFn2, qp_forward, qp_backward, qcqp_forward, qcqp_backward  # noqa: F401
+from ._lib import DiffQCQPError, launch_count  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,265 @@
+// api.cu -- the C ABI declared in include/diffqcqp_b200.h.
+//
+// Thin host layer: argument validation, tile/grid selection, kernel launch on the caller's stream.
+// No CPU compute path exists in this library: every entry point either enqueues sm_100a kernels or
+// returns an error code.
+#include "../../include/diffqcqp_b200.h"
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+std::atomic<long long> g_launches{0};
+
+int cuda_fail(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return DQ_ERR_CUDA;
+}
+
+bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+// Groups (32/T problems each) per single-warp CTA.  The grid should be several waves of the ~148 SMs x
+// resident-CTA capacity so the hardware CTA scheduler balances the skewed iteration counts, while
+// each CTA still has >= 2 groups when the batch is large so the bulk-copy ring has something to
+// prefetch.
+int pick_groups_per_cta(long long n_groups) {
+  const long long target_ctas = 148LL * 32 * 4;
+  long long k = n_groups / target_ctas;
+  if (k < 1) k = 1;
+  if (k > 8) k = 8;
+  return (int)k;
+}
+
+int check_common(const void* P, const void* q, const void* x, long long B, int N) {
+  if (B < 0 || N < 1) return DQ_ERR_BAD_ARG;
+  if (N > DQ_MAX_N) return DQ_ERR_UNSUPPORTED_N;
+  if (B == 0) return DQ_OK;
+  if (!P || !q || !x) return DQ_ERR_BAD_ARG;
+  if (!aligned8(P) || !aligned8(q) || !aligned8(x)) return DQ_ERR_ALIGN;
+  return DQ_OK;
+}
+
+int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n, const double* mu, double* x,
+                 int32_t* iters, long long B, int N, double eps, double mu_prox, int max_iter, int adaptive,
+                 cudaStream_t stream) {
+  int rc = check_common(P, q, x, B, N);
+  if (rc != DQ_OK) return rc;
+  if (qcqp) {
+    if (N % 2 != 0) return DQ_ERR_BAD_ARG;
+    if (B > 0 && (!l_n || !mu)) return DQ_ERR_BAD_ARG;
+    if (!aligned8(l_n) || !aligned8(mu)) return DQ_ERR_ALIGN;
+  }
+  if (B == 0) return DQ_OK;
+  const int T = dq::tile_width(N);
+  const int G = 32 / T;
+  dq::FwdParams p;
+  p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.iters = iters;
+  p.B = B; p.N = N; p.eps = eps; p.mu_prox = mu_prox; p.max_iter = max_iter; p.adaptive = adaptive ? 1 : 0;
+  p.n_groups = (B + G - 1) / G;
+  p.groups_per_cta = pick_groups_per_cta(p.n_groups);
+  const long long grid = (p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta;
+  if (grid > 0x7fffffffLL) return DQ_ERR_BAD_ARG;
+  cudaError_t e = dq::launch_admm_fwd(p, qcqp, T, (unsigned)grid, stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DQ_OK;
+}
+
+int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n, const double* mu,
+                  const double* x, const double* grad_x, double* grad_P, double* grad_q, double* grad_l_n,
+                  double* grad_mu, long long B, int N, cudaStream_t stream) {
+  int rc = check_common(P, q, x, B, N);
+  if (rc != DQ_OK) return rc;
+  if (B > 0 && !grad_x) return DQ_ERR_BAD_ARG;
+  if (!aligned8(grad_x) || !aligned8(grad_P) || !aligned8(grad_q)) return DQ_ERR_ALIGN;
+  if (qcqp) {
+    if (N % 2 != 0) return DQ_ERR_BAD_ARG;
+    if (B > 0 && (!l_n || !mu)) return DQ_ERR_BAD_ARG;
+    if (!aligned8(l_n) || !aligned8(mu) || !aligned8(grad_l_n) || !aligned8(grad_mu)) return DQ_ERR_ALIGN;
+  }
+  if (B == 0) return DQ_OK;
+  if (!grad_P && !grad_q && !(qcqp && (grad_l_n || grad_mu))) return DQ_OK;  // nothing requested
+  const int T = dq::tile_width(N);
+  const int G = 32 / T;
+  dq::BwdParams p;
+  p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.grad_x = grad_x;
+  p.grad_P = grad_P; p.grad_q = grad_q; p.grad_l_n = grad_l_n; p.grad_mu = grad_mu;
+  p.B = B; p.N = N;
+  p.n_groups = (B + G - 1) / G;
+  p.groups_per_cta = pick_groups_per_cta(p.n_groups);
+  const long long grid = (p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta;
+  if (grid > 0x7fffffffLL) return DQ_ERR_BAD_ARG;
+  cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, (unsigned)grid, stream)
+                       : dq::launch_qp_bwd(p, T, (unsigned)grid, stream);
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return DQ_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer path
+// Chunked pipeline over two streams: chunk c's H2D copies, kernels and D2H copies are enqueued on
+// stream c&1, so copies of one chunk overlap the solve of the other.  Device memory comes from the
+// stream-ordered pool (cudaMallocAsync), so repeated calls do not pay cudaMalloc.
+struct HostJob {
+  bool qcqp;
+  const double *P, *q, *l_n, *mu, *grad_x;
+  double *x, *grad_P, *grad_q, *grad_l_n, *grad_mu;
+  long long B;
+  int N;
+  double eps, mu_prox;
+  int max_iter;
+};
+
+#define DQ_CUDA_TRY(expr)                  \
+  do {                                     \
+    cudaError_t _e = (expr);               \
+    if (_e != cudaSuccess) {               \
+      rc = cuda_fail(_e);                  \
+      goto done;                           \
+    }                                      \
+  } while (0)
+
+int solve_host(const HostJob& j, int device) {
+  int rc = DQ_OK;
+  if (j.B < 0 || j.N < 1) return DQ_ERR_BAD_ARG;
+  if (j.N > DQ_MAX_N) return DQ_ERR_UNSUPPORTED_N;
+  if (j.qcqp && (j.N % 2)) return DQ_ERR_BAD_ARG;
+  if (j.B == 0) return DQ_OK;
+  if (!j.P || !j.q || !j.x) return DQ_ERR_BAD_ARG;
+  if (j.qcqp && (!j.l_n || !j.mu)) return DQ_ERR_BAD_ARG;
+  const bool bwd = j.grad_x != nullptr;
+  int prev_dev = -1;
+  cudaStream_t st[2] = {nullptr, nullptr};
+  const int N = j.N, nc = N / 2;
+  const long long NN = (long long)N * N;
+  // chunk size: ~8 chunks, at least 4096 problems each
+  long long chunk = (j.B + 7) / 8;
+  if (chunk < 4096) chunk = 4096;
+  if (chunk > j.B) chunk = j.B;
+  chunk = (chunk + 3) & ~3LL;  // keep chunk starts 16-byte aligned for every N
+  {
+    cudaError_t e = cudaGetDevice(&prev_dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (device >= 0 && device != prev_dev) {
+      e = cudaSetDevice(device);
+      if (e != cudaSuccess) return cuda_fail(e);
+    }
+  }
+  DQ_CUDA_TRY(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
+  DQ_CUDA_TRY(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+  for (long long c0 = 0, ci = 0; c0 < j.B; c0 += chunk, ++ci) {
+    const long long nb = (j.B - c0) < chunk ? (j.B - c0) : chunk;
+    cudaStream_t s = st[ci & 1];
+    double *dP = nullptr, *dq_ = nullptr, *dx = nullptr, *dln = nullptr, *dmu = nullptr, *dg = nullptr,
+           *dgP = nullptr, *dgq = nullptr, *dgl = nullptr, *dgm = nullptr;
+    DQ_CUDA_TRY(cudaMallocAsync(&dP, nb * NN * 8, s));
+    DQ_CUDA_TRY(cudaMallocAsync(&dq_, nb * N * 8, s));
+    DQ_CUDA_TRY(cudaMallocAsync(&dx, nb * N * 8, s));
+    DQ_CUDA_TRY(cudaMemcpyAsync(dP, j.P + c0 * NN, nb * NN * 8, cudaMemcpyHostToDevice, s));
+    DQ_CUDA_TRY(cudaMemcpyAsync(dq_, j.q + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, s));
+    if (j.qcqp) {
+      DQ_CUDA_TRY(cudaMallocAsync(&dln, nb * nc * 8, s));
+      DQ_CUDA_TRY(cudaMallocAsync(&dmu, nb * nc * 8, s));
+      DQ_CUDA_TRY(cudaMemcpyAsync(dln, j.l_n + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, s));
+      DQ_CUDA_TRY(cudaMemcpyAsync(dmu, j.mu + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, s));
+    }
+    rc = forward_impl(j.qcqp, dP, dq_, dln, dmu, dx, nullptr, nb, N, j.eps, j.mu_prox, j.max_iter, 1, s);
+    if (rc != DQ_OK) goto done;
+    DQ_CUDA_TRY(cudaMemcpyAsync(j.x + c0 * N, dx, nb * N * 8, cudaMemcpyDeviceToHost, s));
+    if (bwd) {
+      DQ_CUDA_TRY(cudaMallocAsync(&dg, nb * N * 8, s));
+      DQ_CUDA_TRY(cudaMemcpyAsync(dg, j.grad_x + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, s));
+      if (j.grad_P) DQ_CUDA_TRY(cudaMallocAsync(&dgP, nb * NN * 8, s));
+      if (j.grad_q) DQ_CUDA_TRY(cudaMallocAsync(&dgq, nb * N * 8, s));
+      if (j.qcqp && j.grad_l_n) DQ_CUDA_TRY(cudaMallocAsync(&dgl, nb * nc * 8, s));
+      if (j.qcqp && j.grad_mu) DQ_CUDA_TRY(cudaMallocAsync(&dgm, nb * nc * 8, s));
+      rc = backward_impl(j.qcqp, dP, dq_, dln, dmu, dx, dg, dgP, dgq, dgl, dgm, nb, N, s);
+      if (rc != DQ_OK) goto done;
+      if (dgP) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_P + c0 * NN, dgP, nb * NN * 8, cudaMemcpyDeviceToHost, s));
+      if (dgq) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_q + c0 * N, dgq, nb * N * 8, cudaMemcpyDeviceToHost, s));
+      if (dgl) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_l_n + c0 * nc, dgl, nb * nc * 8, cudaMemcpyDeviceToHost, s));
+      if (dgm) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_mu + c0 * nc, dgm, nb * nc * 8, cudaMemcpyDeviceToHost, s));
+    }
+    double* to_free[] = {dP, dq_, dx, dln, dmu, dg, dgP, dgq, dgl, dgm};
+    for (double* ptr : to_free)
+      if (ptr) DQ_CUDA_TRY(cudaFreeAsync(ptr, s));
+  }
+  DQ_CUDA_TRY(cudaStreamSynchronize(st[0]));
+  DQ_CUDA_TRY(cudaStreamSynchronize(st[1]));
+done:
+  if (st[0]) cudaStreamDestroy(st[0]);
+  if (st[1]) cudaStreamDestroy(st[1]);
+  if (prev_dev >= 0 && device >= 0 && device != prev_dev) cudaSetDevice(prev_dev);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dq_version(void) { return 100; /* 0.1.0 */ }
+const char* dq_build_arch(void) { return "sm_100a"; }
+int dq_max_n(void) { return DQ_MAX_N; }
+int dq_last_cuda_error(void) { return g_last_cuda_error; }
+int64_t dq_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+const char* dq_error_string(int code) {
+  switch (code) {
+    case DQ_OK: return "ok";
+    case DQ_ERR_BAD_ARG: return "bad argument (null pointer, negative batch, N < 1, or odd N for the QCQP)";
+    case DQ_ERR_UNSUPPORTED_N: return "N exceeds DQ_MAX_N (one problem must fit one warp tile)";
+    case DQ_ERR_ALIGN: return "pointer is not 8-byte aligned";
+    case DQ_ERR_CUDA: return "CUDA runtime error (see dq_last_cuda_error)";
+    default: return "unknown error code";
+  }
+}
+
+int dq_qp_forward(const double* P, const double* q, const double* warm_start, double* x, int32_t* iters,
+                  int64_t B, int32_t N, double eps, double mu_prox, int32_t max_iter, int32_t adaptative_rho,
+                  void* stream) {
+  (void)warm_start;  // dead in the reference: Solver.cpp:70 -> :80
+  return forward_impl(false, P, q, nullptr, nullptr, x, iters, B, N, eps, mu_prox, max_iter, adaptative_rho,
+                      (cudaStream_t)stream);
+}
+
+int dq_qp_backward(const double* P, const double* q, const double* x, const double* grad_x, double* grad_P,
+                   double* grad_q, int64_t B, int32_t N, void* stream) {
+  return backward_impl(false, P, q, nullptr, nullptr, x, grad_x, grad_P, grad_q, nullptr, nullptr, B, N,
+                       (cudaStream_t)stream);
+}
+
+int dq_qcqp_forward(const double* P, const double* q, const double* l_n, const double* mu,
+                    const double* warm_start, double* x, int32_t* iters, int64_t B, int32_t N, double eps,
+                    double mu_prox, int32_t max_iter, int32_t adaptative_rho, void* stream) {
+  (void)warm_start;  // dead in the reference: Solver.cpp:529 -> :539
+  return forward_impl(true, P, q, l_n, mu, x, iters, B, N, eps, mu_prox, max_iter, adaptative_rho,
+                      (cudaStream_t)stream);
+}
+
+int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const double* mu, const double* x,
+                     const double* grad_x, double* grad_P, double* grad_q, double* grad_l_n, double* grad_mu,
+                     int64_t B, int32_t N, void* stream) {
+  return backward_impl(true, P, q, l_n, mu, x, grad_x, grad_P, grad_q, grad_l_n, grad_mu, B, N,
+                       (cudaStream_t)stream);
+}
+
+int dq_qp_solve_host(const double* P, const double* q, double* x, const double* grad_x, double* grad_P,
+                     double* grad_q, int64_t B, int32_t N, double eps, double mu_prox, int32_t max_iter,
+                     int32_t device) {
+  HostJob j{false, P, q, nullptr, nullptr, grad_x, x, grad_P, grad_q, nullptr, nullptr, B, N, eps, mu_prox, max_iter};
+  return solve_host(j, device);
+}
+
+int dq_qcqp_solve_host(const double* P, const double* q, const double* l_n, const double* mu, double* x,
+                       const double* grad_x, double* grad_P, double* grad_q, double* grad_l_n, double* grad_mu,
+                       int64_t B, int32_t N, double eps, double mu_prox, int32_t max_iter, int32_t device) {
+  HostJob j{true, P, q, l_n, mu, grad_x, x, grad_P, grad_q, grad_l_n, grad_mu, B, N, eps, mu_prox, max_iter};
+  return solve_host(j, device);
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// common.cuh -- warp-tile building blocks shared by the sm_100a kernels.
+//
+// Execution model: one *tile* of T lanes (T = 8, 16 or 32, the next power of two
+// >= N, minimum 8) owns one problem; lane i of the tile owns element i of every N-vector and row i of
+// every N x N matrix.  A warp therefore carries G = 32/T problems ("a group").  Each CTA is a single
+// warp, so there is no CTA-level synchronisation anywhere: only __syncwarp and tile-local shuffles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dq {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// ---------------------------------------------------------------- tile reductions (xor butterflies)
+// Every lane of the tile ends with the bitwise-identical result (max/add are commutative and both
+// partners of a butterfly stage compute the same pair), so per-problem control flow stays uniform.
+template <int T>
+__device__ __forceinline__ double tile_max(double v) {
+#pragma unroll
+  for (int o = T / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+
+template <int T>
+__device__ __forceinline__ double tile_sum(double v) {
+#pragma unroll
+  for (int o = T / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+// Two max-reductions for the price of ~1.3: after the first exchange even lanes carry `a`, odd lanes
+// carry `b`; the remaining stages reduce one value per lane; a final exchange hands both back.
+template <int T>
+__device__ __forceinline__ void tile_max2(double& a, double& b, int lane) {
+  const bool odd = lane & 1;
+  double send = odd ? a : b;
+  double keep = odd ? b : a;
+  double got = __shfl_xor_sync(FULL_MASK, send, 1);
+  double v = fmax(keep, got);  // even lanes: max(a_even, a_odd); odd lanes: max(b_odd, b_even)
+#pragma unroll
+  for (int o = T / 2; o > 1; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+  double other = __shfl_xor_sync(FULL_MASK, v, 1);
+  a = odd ? other : v;
+  b = odd ? v : other;
+}
+
+// ---------------------------------------------------------------- mbarrier + 1-D bulk copy (TMA)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`.  dst/src 16-byte aligned,
+// bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// Stage `count` doubles from global into shared memory.  Bulk (TMA) when both ends are 16-byte
+// aligned and the size is a multiple of 16 bytes -- returns the byte count the caller must have
+// announced with mbar_expect_tx -- otherwise an element-wise copy by the whole warp (returns 0).
+// Call with all 32 lanes.
+__device__ __forceinline__ bool bulk_eligible(const void* src, const void* dst, size_t bytes) {
+  return ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0 && bytes > 0;
+}
+
+__device__ __forceinline__ void warp_copy(double* dst, const double* __restrict__ src, int count, int lane) {
+  for (int i = lane; i < count; i += 32) dst[i] = __ldg(src + i);
+}
+
+// ---------------------------------------------------------------- in-tile SPD inverse
+// Mirrors the reference's `chol = M.llt(); Minv.setIdentity(); chol.solveInPlace(Minv)`
+// (Solver.cpp:76-77, :22-23): Cholesky factor, then forward and backward substitution against the
+// identity.  Lane i enters with a[0..i] = lower-triangular part of row i of M (a[i] = diagonal) and
+// leaves with out[0..T) = row i of M^{-1} (= column i, M^{-1} is symmetric).
+//
+// Lb   : this tile's T x T shared scratch (row stride T).  Entries with an index >= N must be zero
+//        on entry and are never written, so padded lanes/columns drop out of every sum.
+// dinv : this tile's T-entry shared scratch for the reciprocal pivots (entries >= N zero).
+// The factor is stored symmetrically (Lb[i][k] = Lb[k][i] = L(i,k)) so both substitutions read rows,
+// all lanes the same address (shared-memory broadcast), vectorisable to 128-bit loads.
+template <int T>
+__device__ __forceinline__ void tile_spd_inverse(double (&a)[T], double (&out)[T], double* Lb, double* dinv,
+                                                 int N, int ti, int tile_base_lane) {
+  // ---- Cholesky, left-looking, one column per step (Eigen LLT unblocked order)
+#pragma unroll
+  for (int k = 0; k < T; k++) {
+    if (k < N) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < k; j++) acc = fma(a[j], Lb[k * T + j], acc);
+      double s = a[k] - acc;
+      double skk = __shfl_sync(FULL_MASK, s, tile_base_lane + k);
+      double piv = sqrt(skk);
+      double val = (ti == k) ? piv : s / piv;
+      a[k] = val;
+      if (ti >= k && ti < N) {
+        Lb[ti * T + k] = val;
+        Lb[k * T + ti] = val;
+      }
+      if (ti == k) dinv[k] = 1.0 / piv;
+      __syncwarp();
+    }
+  }
+  // ---- forward substitution L y = e_ti
+#pragma unroll
+  for (int i = 0; i < T; i++) {
+    if (i < N) {
+      double acc = (i == ti) ? 1.0 : 0.0;
+#pragma unroll
+      for (int j = 0; j < i; j++) acc = fma(-Lb[i * T + j], out[j], acc);
+      out[i] = acc * dinv[i];
+    } else {
+      out[i] = 0.0;
+    }
+  }
+  // ---- back substitution L^T x = y   (L^T(i,j) = L(j,i) = Lb[i][j] for j > i)
+#pragma unroll
+  for (int i = T - 1; i >= 0; i--) {
+    if (i < N) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = i + 1; j < T; j++) acc = fma(Lb[i * T + j], out[j], acc);
+      out[i] = (out[i] - acc) * dinv[i];
+    }
+  }
+}
+
+// y_i = sum_j row[j] * vb[j]  with vb a T-entry shared vector (same for all lanes of the tile).
+template <int T>
+__device__ __forceinline__ double tile_row_dot(const double (&row)[T], const double* vb, int N) {
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < T; j += 2) {
+    if (j < N) {
+      double2 v = *reinterpret_cast<const double2*>(vb + j);
+      acc = fma(row[j], v.x, acc);
+      acc = fma(row[j + 1], v.y, acc);
+    }
+  }
+  return acc;
+}
+
+}  // namespace dq

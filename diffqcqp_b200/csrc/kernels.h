@@ -1,0 +1,51 @@
+// kernels.h -- host-visible launch interface of the sm_100a kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace dq {
+
+struct FwdParams {
+  const double* P;
+  const double* q;
+  const double* l_n;  // QCQP only
+  const double* mu;   // QCQP only
+  double* x;
+  int32_t* iters;  // nullable
+  long long B;
+  int N;
+  double eps;
+  double mu_prox;
+  int max_iter;
+  int adaptive;
+  int groups_per_cta;
+  long long n_groups;
+};
+
+struct BwdParams {
+  const double* P;
+  const double* q;
+  const double* l_n;  // QCQP only
+  const double* mu;   // QCQP only
+  const double* x;
+  const double* grad_x;
+  double* grad_P;    // nullable
+  double* grad_q;    // nullable
+  double* grad_l_n;  // nullable, QCQP only
+  double* grad_mu;   // nullable, QCQP only
+  long long B;
+  int N;
+  int groups_per_cta;
+  long long n_groups;
+};
+
+// T = tile width (8, 16 or 32 lanes per problem); a warp carries 32/T problems.
+inline int tile_width(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
+
+size_t fwd_smem_bytes(int T, int N, bool qcqp);
+cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, unsigned grid, cudaStream_t stream);
+cudaError_t launch_qp_bwd(const BwdParams& p, int T, unsigned grid, cudaStream_t stream);
+cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, unsigned grid, cudaStream_t stream);
+
+}  // namespace dq

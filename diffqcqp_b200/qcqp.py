@@ -1,0 +1,189 @@
+"""Drop-in for the hot path of the reference's ``qcqp.py``: ``QPFn2`` and ``QCQPFn2``.
+
+Same class names, argument order, tensor shapes and gradient-tuple arity as the reference
+(qcqp.py:22-52 and :141-181).  What differs is what runs underneath: instead of a Python loop over the
+batch calling a per-problem C++ solver (qcqp.py:29-31, :45-47, :149-151, :167-168), each of
+forward / backward is ONE launch of an sm_100a CUDA kernel over the whole batch through the C ABI in
+``include/diffqcqp_b200.h``.
+
+Devices.  The reference is CPU-only (``.numpy()`` at qcqp.py:30).  Here:
+  * CUDA tensors in -> CUDA tensors out, asynchronous on the current stream, no host sync;
+  * CPU tensors in (what a user of the reference has) -> inputs are copied to the current CUDA
+    device, solved there, and the result is returned as a CPU tensor; device copies are kept on the
+    autograd context so backward only moves ``grad_l`` in and the gradients out.
+There is no CPU compute path: without the CUDA extension or a CUDA device this raises.
+
+Notes carried over from the reference's behaviour:
+  * ``warm_start`` is accepted and ignored, as in the reference (Solver.cpp:70 -> :80 overwrites it).
+  * backward uses the binding's default ``epsilon=1e-10`` regardless of the forward ``eps``
+    (qcqp.py:47,168; pybindings.cpp:80,82).
+  * ``adaptative_rho`` is fixed to True (qcqp.py:27,148).
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+__all__ = ["QPFn2", "QCQPFn2", "qp_forward", "qp_backward", "qcqp_forward", "qcqp_backward"]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _as_dev(t: torch.Tensor, device, name: str) -> torch.Tensor:
+    """fp64, contiguous, on `device`, 16-byte aligned (the bulk-copy path wants that)."""
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.dtype.is_floating_point:
+        raise ValueError(f"{name} must be a floating-point tensor, got {t.dtype}")
+    t = t.detach()
+    if t.device != device or t.dtype != torch.float64:
+        t = t.to(device=device, dtype=torch.float64, non_blocking=True)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def _compute_device(*tensors) -> torch.device:
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise _lib.DiffQCQPError(
+            "diffqcqp_b200 needs a CUDA device (sm_100a); there is no CPU fallback in the product path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _check_shapes(P, q, l_n=None, mu=None):
+    if P.dim() != 3 or P.size(1) != P.size(2):
+        raise ValueError(f"P must have shape (B,N,N), got {tuple(P.shape)}")
+    B, N = P.size(0), P.size(1)
+    if q.dim() != 3 or tuple(q.shape) != (B, N, 1):
+        raise ValueError(f"q must have shape (B,N,1)=({B},{N},1), got {tuple(q.shape)}")
+    if l_n is not None:
+        if N % 2:
+            raise ValueError(f"the QCQP needs an even N (two tangential components per contact), got N={N}")
+        for nm, t in (("l_n", l_n), ("mu", mu)):
+            if tuple(t.shape) != (B, N // 2, 1):
+                raise ValueError(f"{nm} must have shape (B,N/2,1)=({B},{N // 2},1), got {tuple(t.shape)}")
+    return B, N
+
+
+# --------------------------------------------------------------------------- raw batched ops
+def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False):
+    """Batched solveQP on CUDA tensors: P (B,N,N), q (B,N,1) -> x (B,N,1) [, iters (B,) int32]."""
+    dev = P.device
+    B, N = P.size(0), P.size(1)
+    x = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
+    iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
+    L = _lib.load()
+    with torch.cuda.device(dev):
+        rc = L.dq_qp_forward(_ptr(P), _ptr(q), None, _ptr(x), _ptr(iters), B, N, float(eps), float(mu_prox),
+                             int(max_iter), int(bool(adaptative_rho)), _stream_ptr(dev))
+    _lib.check(rc, "dq_qp_forward")
+    return (x, iters) if return_iters else x
+
+
+def qp_backward(P, q, x, grad_x, need_P=True, need_q=True):
+    dev = P.device
+    B, N = P.size(0), P.size(1)
+    gP = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need_P else None
+    gq = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if need_q else None
+    if need_P or need_q:
+        L = _lib.load()
+        with torch.cuda.device(dev):
+            rc = L.dq_qp_backward(_ptr(P), _ptr(q), _ptr(x), _ptr(grad_x), _ptr(gP), _ptr(gq), B, N,
+                                  _stream_ptr(dev))
+        _lib.check(rc, "dq_qp_backward")
+    return gP, gq
+
+
+def qcqp_forward(P, q, l_n, mu, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False):
+    dev = P.device
+    B, N = P.size(0), P.size(1)
+    x = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
+    iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
+    L = _lib.load()
+    with torch.cuda.device(dev):
+        rc = L.dq_qcqp_forward(_ptr(P), _ptr(q), _ptr(l_n), _ptr(mu), None, _ptr(x), _ptr(iters), B, N,
+                               float(eps), float(mu_prox), int(max_iter), int(bool(adaptative_rho)),
+                               _stream_ptr(dev))
+    _lib.check(rc, "dq_qcqp_forward")
+    return (x, iters) if return_iters else x
+
+
+def qcqp_backward(P, q, l_n, mu, x, grad_x, need=(True, True, True, True)):
+    dev = P.device
+    B, N = P.size(0), P.size(1)
+    nc = N // 2
+    gP = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need[0] else None
+    gq = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if need[1] else None
+    gl = torch.empty((B, nc, 1), dtype=torch.float64, device=dev) if need[2] else None
+    gm = torch.empty((B, nc, 1), dtype=torch.float64, device=dev) if need[3] else None
+    if any(need):
+        L = _lib.load()
+        with torch.cuda.device(dev):
+            rc = L.dq_qcqp_backward(_ptr(P), _ptr(q), _ptr(l_n), _ptr(mu), _ptr(x), _ptr(grad_x), _ptr(gP),
+                                    _ptr(gq), _ptr(gl), _ptr(gm), B, N, _stream_ptr(dev))
+        _lib.check(rc, "dq_qcqp_backward")
+    return gP, gq, gl, gm
+
+
+def _back_to(t, device):
+    if t is None or t.device == device:
+        return t
+    return t.to(device)
+
+
+# --------------------------------------------------------------------------- autograd surface
+class QPFn2(Function):
+    """min 1/2 l'Pl + q'l  s.t. l >= 0, batched.  Mirrors qcqp.py:22-52."""
+
+    @staticmethod
+    def forward(ctx, P, q, warm_start, eps, max_iter, mu_prox=1e-7):
+        _check_shapes(P, q)
+        dev = _compute_device(P, q)
+        Pd, qd = _as_dev(P, dev, "P"), _as_dev(q, dev, "q")
+        x = qp_forward(Pd, qd, eps, max_iter, mu_prox, True)
+        ctx.save_for_backward(Pd, qd, x)
+        ctx.out_device = q.device
+        return _back_to(x, q.device)
+
+    @staticmethod
+    def backward(ctx, grad_l):
+        Pd, qd, x = ctx.saved_tensors
+        g = _as_dev(grad_l, Pd.device, "grad_l")
+        gP, gq = qp_backward(Pd, qd, x, g, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return _back_to(gP, ctx.out_device), _back_to(gq, ctx.out_device), None, None, None, None
+
+
+class QCQPFn2(Function):
+    """min 1/2 l'Pl + q'l  s.t. |(l_2i, l_2i+1)| <= l_n[i] mu[i], batched.  Mirrors qcqp.py:141-181."""
+
+    @staticmethod
+    def forward(ctx, P, q, l_n, mu, warm_start, eps, max_iter, mu_prox=1e-7):
+        _check_shapes(P, q, l_n, mu)
+        dev = _compute_device(P, q, l_n, mu)
+        Pd, qd = _as_dev(P, dev, "P"), _as_dev(q, dev, "q")
+        ld, md = _as_dev(l_n, dev, "l_n"), _as_dev(mu, dev, "mu")
+        x = qcqp_forward(Pd, qd, ld, md, eps, max_iter, mu_prox, True)
+        ctx.save_for_backward(Pd, qd, ld, md, x)
+        ctx.out_device = q.device
+        return _back_to(x, q.device)
+
+    @staticmethod
+    def backward(ctx, grad_l):
+        Pd, qd, ld, md, x = ctx.saved_tensors
+        g = _as_dev(grad_l, Pd.device, "grad_l")
+        gP, gq, gl, gm = qcqp_backward(Pd, qd, ld, md, x, g, tuple(ctx.needs_input_grad[:4]))
+        o = ctx.out_device
+        return _back_to(gP, o), _back_to(gq, o), _back_to(gl, o), _back_to(gm, o), None, None, None, None

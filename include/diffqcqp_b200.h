@@ -1,0 +1,107 @@
+/*
+ * diffqcqp_b200.h -- C ABI of the B200 (sm_100a) batched differentiable ADMM QP/QCQP solver.
+ *
+ * This is the drop-in boundary for the hot path of quentinll/diffqcqp.  Each entry point
+ * replaces one of the reference's per-problem pybind11 functions *together with* the Python
+ * per-item loop that calls it, i.e. it takes the whole batch:
+ *
+ *   dq_qp_forward     <- solveQP               pybindings.cpp:17-22,76   + loop qcqp.py:29-31
+ *   dq_qp_backward    <- solveDerivativesQP    pybindings.cpp:24-30,80   + loop qcqp.py:45-51
+ *   dq_qcqp_forward   <- solveQCQP             pybindings.cpp:54-60,79   + loop qcqp.py:149-151
+ *   dq_qcqp_backward  <- solveDerivativesQCQP  pybindings.cpp:62-71,82   + loop qcqp.py:167-180
+ *
+ * Layout (all fp64, contiguous, row-major, exactly the reference's tensors):
+ *   P (B,N,N)   q, warm_start, x, grad_x, grad_q (B,N[,1])   l_n, mu, grad_l_n, grad_mu (B,N/2[,1])
+ *   grad_P (B,N,N).
+ *
+ * Device entry points take DEVICE pointers and a CUDA stream (cudaStream_t passed as void*, NULL =
+ * legacy default stream); they only enqueue work and never synchronise.  *_host entry points take
+ * HOST pointers, stage through pinned buffers and return when the outputs are in host memory.
+ *
+ * Pointers must be 8-byte aligned; 16-byte aligned base pointers enable the bulk-copy (TMA) stage-in
+ * (otherwise a slower element-wise stage-in is used, same results).
+ *
+ * Return value: DQ_OK or a DQ_ERR_* code (dq_error_string gives text).  Nothing is thrown.
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns DQ_ERR_CUDA.
+ */
+#ifndef DIFFQCQP_B200_H
+#define DIFFQCQP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DQ_OK 0
+#define DQ_ERR_BAD_ARG 1      /* null required pointer, B < 0, N < 1, odd N for the QCQP, ...      */
+#define DQ_ERR_UNSUPPORTED_N 2 /* N above DQ_MAX_N                                                 */
+#define DQ_ERR_ALIGN 3        /* pointer not 8-byte aligned                                       */
+#define DQ_ERR_CUDA 4         /* CUDA runtime error; dq_last_cuda_error() has the code            */
+
+#define DQ_MAX_N 32           /* one problem lives in one warp tile: N <= 32 (QCQP: <= 16 contacts) */
+
+/* Library / build identification. */
+int dq_version(void);                 /* 10000*major + 100*minor + patch                          */
+const char* dq_build_arch(void);      /* "sm_100a"                                                */
+const char* dq_error_string(int code);
+int dq_last_cuda_error(void);         /* cudaError_t of the last DQ_ERR_CUDA on this thread       */
+int dq_max_n(void);                   /* DQ_MAX_N                                                 */
+
+/*
+ * Forward ADMM solve of   min 1/2 x'Px + q'x  s.t. x >= 0      (Solver.cpp:61-123).
+ *   warm_start : accepted for signature parity, never read -- the reference overwrites it before
+ *                use (Solver.cpp:70 -> :80); may be NULL.
+ *   iters      : optional (B) int32 output, ADMM iterations executed per problem; may be NULL.
+ *   eps, mu_prox, max_iter, adaptative_rho : as solveQP's arguments (pybindings.cpp:76).
+ */
+int dq_qp_forward(const double* P, const double* q, const double* warm_start, double* x,
+                  int32_t* iters, int64_t B, int32_t N, double eps, double mu_prox,
+                  int32_t max_iter, int32_t adaptative_rho, void* stream);
+
+/*
+ * Backward of the QP: dl = solveDerivativesQP(P,q,x,grad_x) with epsilon = 1e-10 (the binding's
+ * default, qcqp.py:47 never passes one), then grad_P = -dl x' and grad_q = -dl (qcqp.py:48-51).
+ * grad_P / grad_q may each be NULL (ctx.needs_input_grad gating).
+ */
+int dq_qp_backward(const double* P, const double* q, const double* x, const double* grad_x,
+                   double* grad_P, double* grad_q, int64_t B, int32_t N, void* stream);
+
+/*
+ * Forward ADMM solve of   min 1/2 x'Px + q'x  s.t. |(x_2i, x_2i+1)| <= l_n[i]*mu[i]
+ * (pybindings.cpp:54-60, Solver.cpp:505-582).  N must be even; l_n, mu are (B, N/2).
+ */
+int dq_qcqp_forward(const double* P, const double* q, const double* l_n, const double* mu,
+                    const double* warm_start, double* x, int32_t* iters, int64_t B, int32_t N,
+                    double eps, double mu_prox, int32_t max_iter, int32_t adaptative_rho,
+                    void* stream);
+
+/*
+ * Backward of the QCQP (pybindings.cpp:62-71, Solver.cpp:584-691, qcqp.py:170-180):
+ * grad_P = -dl x', grad_q = -dl, grad_l_n = E2 dgamma, grad_mu = E1 dgamma.  Any output may be NULL.
+ */
+int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const double* mu,
+                     const double* x, const double* grad_x, double* grad_P, double* grad_q,
+                     double* grad_l_n, double* grad_mu, int64_t B, int32_t N, void* stream);
+
+/*
+ * Host-buffer convenience path (what a caller holding CPU arrays, like the reference's users,
+ * calls): copies inputs host->device through pinned staging in chunks that overlap with the
+ * solve, runs forward (and, when grad_x != NULL, backward) and copies results back.
+ * Outputs that are NULL are skipped.  device < 0 means the current device.
+ */
+int dq_qp_solve_host(const double* P, const double* q, double* x, const double* grad_x,
+                     double* grad_P, double* grad_q, int64_t B, int32_t N, double eps,
+                     double mu_prox, int32_t max_iter, int32_t device);
+int dq_qcqp_solve_host(const double* P, const double* q, const double* l_n, const double* mu,
+                       double* x, const double* grad_x, double* grad_P, double* grad_q,
+                       double* grad_l_n, double* grad_mu, int64_t B, int32_t N, double eps,
+                       double mu_prox, int32_t max_iter, int32_t device);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+int64_t dq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFQCQP_B200_H */
