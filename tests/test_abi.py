@@ -1,0 +1,133 @@
+"""CPU tests of the C-ABI boundary and the host-side mirror of the reference surface (no GPU compute)."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from diffqcqp_b200 import _lib, build
+    build.build()  # nvcc cross-compiles without a GPU
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "diffqcqp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from diffqcqp_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/diffqcqp_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == syms
+
+
+def test_identification(lib):
+    assert lib.dq_build_arch() == b"sm_100a"
+    assert lib.dq_version() >= 100
+    assert lib.dq_max_n() == 32
+    assert lib.dq_error_string(0) == b"ok"
+    for code in (1, 2, 3, 4):
+        assert len(lib.dq_error_string(code)) > 3
+
+
+def test_sass_is_sm100a_and_uses_bulk_copies():
+    from diffqcqp_b200 import _lib
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_argument_validation_without_gpu(lib):
+    buf = np.zeros(64 * 64 + 64, dtype=np.float64)
+    p = buf.ctypes.data
+    DQ_OK, BAD, UNSUP, ALIGN = 0, 1, 2, 3
+    # empty batch is a no-op success (no launch, so no device needed)
+    assert lib.dq_qp_forward(p, p, None, p, None, 0, 8, 1e-7, 1e-7, 10, 1, None) == DQ_OK
+    assert lib.dq_qcqp_forward(p, p, p, p, None, p, None, 0, 8, 1e-7, 1e-7, 10, 1, None) == DQ_OK
+    assert lib.dq_qp_backward(p, p, p, p, p, p, 0, 8, None) == DQ_OK
+    # bad arguments are rejected before anything touches CUDA
+    assert lib.dq_qp_forward(None, p, None, p, None, 4, 8, 1e-7, 1e-7, 10, 1, None) == BAD
+    assert lib.dq_qp_forward(p, p, None, p, None, -1, 8, 1e-7, 1e-7, 10, 1, None) == BAD
+    assert lib.dq_qp_forward(p, p, None, p, None, 4, 0, 1e-7, 1e-7, 10, 1, None) == BAD
+    assert lib.dq_qp_forward(p, p, None, p, None, 4, 33, 1e-7, 1e-7, 10, 1, None) == UNSUP
+    assert lib.dq_qp_forward(p + 4, p, None, p, None, 4, 8, 1e-7, 1e-7, 10, 1, None) == ALIGN
+    assert lib.dq_qcqp_forward(p, p, p, p, None, p, None, 4, 7, 1e-7, 1e-7, 10, 1, None) == BAD  # odd N
+    assert lib.dq_qcqp_forward(p, p, None, p, None, p, None, 4, 8, 1e-7, 1e-7, 10, 1, None) == BAD
+    assert lib.dq_qp_backward(p, p, p, None, p, p, 4, 8, None) == BAD
+    assert lib.dq_qcqp_backward(p, p, p, p, p, p, p, p, p, p, 4, 9, None) == BAD
+    assert lib.dq_qp_solve_host(p, p, p, None, None, None, 4, 40, 1e-7, 1e-7, 10, -1) == UNSUP
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    """Without a device the product path must fail loudly, never compute on the CPU."""
+    import qcqp
+    from diffqcqp_b200 import DiffQCQPError
+    P = torch.diag_embed(torch.rand(4, 8)); q = torch.rand(4, 8, 1)
+    with pytest.raises(DiffQCQPError):
+        qcqp.QPFn2.apply(P, q, torch.zeros_like(q), 1e-7, 100)
+    buf = np.ones(4 * 64 + 64, dtype=np.float64)
+    p = buf.ctypes.data
+    assert lib.dq_qp_forward(p, p, None, p, None, 4, 8, 1e-7, 1e-7, 10, 1, None) == 4  # DQ_ERR_CUDA
+    assert lib.dq_last_cuda_error() != 0
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "diffqcqp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower().replace("# no oracle", ""), f"{f} mentions the oracle"
+    src = open(os.path.join(ROOT, "qcqp.py")).read()
+    assert "oracle" not in src
+
+
+def test_surface_mirrors_reference_signatures():
+    import qcqp
+    sig = inspect.signature(qcqp.QPFn2.forward)
+    assert list(sig.parameters) == ["ctx", "P", "q", "warm_start", "eps", "max_iter", "mu_prox"]   # qcqp.py:24
+    assert sig.parameters["mu_prox"].default == 1e-7
+    sig = inspect.signature(qcqp.QCQPFn2.forward)
+    assert list(sig.parameters) == ["ctx", "P", "q", "l_n", "mu", "warm_start", "eps", "max_iter", "mu_prox"]  # :144
+    assert torch.get_default_dtype() == torch.float64                                               # qcqp.py:13
+
+
+def test_shape_validation():
+    from diffqcqp_b200.qcqp import _check_shapes
+    P, q = torch.zeros(3, 8, 8), torch.zeros(3, 8, 1)
+    assert _check_shapes(P, q) == (3, 8)
+    with pytest.raises(ValueError):
+        _check_shapes(torch.zeros(3, 8, 7), q)
+    with pytest.raises(ValueError):
+        _check_shapes(P, torch.zeros(3, 8))
+    with pytest.raises(ValueError):
+        _check_shapes(torch.zeros(3, 7, 7), torch.zeros(3, 7, 1), torch.zeros(3, 3, 1), torch.zeros(3, 3, 1))
+    with pytest.raises(ValueError):
+        _check_shapes(P, q, torch.zeros(3, 3, 1), torch.zeros(3, 4, 1))
+    assert _check_shapes(P, q, torch.zeros(3, 4, 1), torch.zeros(3, 4, 1)) == (3, 8)
+
+
+def test_algorithmic_bytes_match_survey():
+    from diffqcqp_b200 import workloads as wl
+    # SURVEY.md section 8d minus the dead warm_start read (8N) that the kernels never perform
+    assert wl.qp_bytes(8) == 1984 - 64
+    assert wl.qcqp_bytes(16) == 7424 - 128
+    assert wl.qcqp_bytes(24) == 15744 - 192
+    assert wl.qp_bytes(32) == 26368 - 256

