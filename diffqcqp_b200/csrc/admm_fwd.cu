@@ -5,347 +5,368 @@
 //   pybindings.cpp:17-22 / :54-60 (mul_n = l_n o mu)
 //   Solver.cpp:46-59 power_iteration, :61-123 solveQP, :505-519 prox_circle, :521-582 solveQCQP
 //
-// One warp per CTA; a tile of T lanes per problem; everything after the stage-in lives in registers
-// and in the warp's private shared-memory scratch.  Convergence is decided per tile from tile-wide
-// max-reductions and the warp keeps iterating while a ballot says any tile is live -- there is no
-// host round trip and no CTA barrier.  Inputs arrive through 1-D bulk copies (TMA, cp.async.bulk)
-// into a two-stage shared-memory ring so the next group's P,q are in flight while this one iterates.
+// Execution model.  A tile of T lanes owns one problem (lane i = element i / row i), a warp carries
+// G = 32/T problems and handles exactly one such group, so the hardware CTA scheduler balances the
+// skewed iteration counts at warp granularity.  Warps never synchronise with each other.  Each lane
+// pulls its own row of P straight from global memory into registers with 256-bit loads (a warp
+// reads one contiguous 32*T*8-byte slab), decides from the data whether the group is diagonal, and
+// then iterates entirely in registers; convergence is decided per tile from tile-wide reductions and
+// the warp leaves the loop when a ballot says every tile is done -- no host round trip.
+//
+// Arithmetic.  The element-wise ADMM updates use explicitly rounded operations (__dmul_rn/__dadd_rn,
+// never contracted into FMAs) in the reference's evaluation order, and u/rho is an exact IEEE
+// quotient (reciprocal + one FMA correction), so for diagonal P the iterates are bit-identical to a
+// non-FMA x86-64 build of the reference up to the value of pow() and the association of the norms in
+// power_iteration.  Dense matrix-vector products and the Cholesky use FMAs (Eigen's own summation
+// order is packetised, so there is no bit-level target there).
 #include "common.cuh"
 #include "kernels.h"
 
 namespace dq {
 
+constexpr int FWD_WARPS = 4;  // warps per CTA (independent; no CTA-level barrier anywhere)
+
 template <int T>
 struct FwdSmem {
-  // per-stage sizes in doubles, for runtime N
-  __device__ __host__ static size_t stage_doubles(int N, bool qcqp) {
-    const int G = 32 / T;
-    size_t p = (size_t)G * N * N, q = (size_t)G * N, c = qcqp ? (size_t)G * (N / 2) : 0;
-    // each array rounded up to an even number of doubles so every array starts 16-byte aligned
-    return ((p + 1) & ~(size_t)1) + ((q + 1) & ~(size_t)1) + 2 * ((c + 1) & ~(size_t)1);
-  }
-  __device__ __host__ static size_t total_bytes(int N, bool qcqp) {
-    // 2 stages + Lbuf (32*T) + vbuf (32) + dinv (32) doubles + 2 mbarriers
-    return (2 * stage_doubles(N, qcqp) + 32 * T + 32 + 32) * sizeof(double) + 2 * sizeof(uint64_t);
-  }
+  // per warp: Cholesky scratch [G][T][T] = 32*T, gemv vector double-buffered 2*32, reciprocal pivots 32
+  static constexpr int per_warp_doubles = 32 * T + 3 * 32;
+  static constexpr size_t bytes = (size_t)FWD_WARPS * per_warp_doubles * sizeof(double);
 };
 
-size_t fwd_smem_bytes(int T, int N, bool qcqp) {
+size_t fwd_smem_bytes(int T) {
   switch (T) {
-    case 8: return FwdSmem<8>::total_bytes(N, qcqp);
-    case 16: return FwdSmem<16>::total_bytes(N, qcqp);
-    default: return FwdSmem<32>::total_bytes(N, qcqp);
+    case 8: return FwdSmem<8>::bytes;
+    case 16: return FwdSmem<16>::bytes;
+    default: return FwdSmem<32>::bytes;
   }
 }
 
+// a / b given rb = RN(1/b): the correctly rounded IEEE quotient (Markstein's correction step).
+__device__ __forceinline__ double div_by(double a, double b, double rb) {
+  const double q0 = __dmul_rn(a, rb);
+  const double r = __fma_rn(-q0, b, a);
+  return __fma_rn(r, rb, q0);
+}
+
+// Row `ti` of one problem's P into registers.  N == T and a 32-byte aligned base take 256-bit loads.
+template <int T>
+__device__ __forceinline__ void load_row(double (&row)[T], const double* __restrict__ src, int N, bool valid,
+                                         bool vec32) {
+#pragma unroll
+  for (int j = 0; j < T; j++) row[j] = 0.0;
+  if (!valid) return;
+  if (N == T && vec32) {
+#pragma unroll
+    for (int j = 0; j < T; j += 4) {
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                   : "=d"(row[j]), "=d"(row[j + 1]), "=d"(row[j + 2]), "=d"(row[j + 3])
+                   : "l"(src + j));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < T; j++)
+      if (j < N) row[j] = __ldg(src + j);
+  }
+}
+
+// y_i = sum_j row[j] * vb[j], vb a T-entry shared vector (entries >= N are zero), in chunks of 8 so
+// that N = 24 on a 32-lane tile skips the last quarter.
+template <int T>
+__device__ __forceinline__ double row_dot(const double (&row)[T], const double* vb, int N) {
+  double acc = 0.0;
+#pragma unroll
+  for (int j0 = 0; j0 < T; j0 += 8) {
+    if (j0 < N) {
+#pragma unroll
+      for (int j = j0; j < j0 + 8; j += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(vb + j);
+        acc = fma(row[j], v.x, acc);
+        acc = fma(row[j + 1], v.y, acc);
+      }
+    }
+  }
+  return acc;
+}
+
+// Tile maxima of two non-negative quantities at once (sign bits are dropped, i.e. |a|, |b|).  Non-negative
+// doubles order like their bit patterns, so the reduction runs on 64-bit integers (ALU pipe, no NaN
+// fix-up code): after the first exchange even lanes carry `a`, odd lanes carry `b`, the remaining
+// butterfly stages reduce one value per lane and a final exchange hands both back.  Every lane of the
+// tile ends with bit-identical results, which keeps the per-problem control flow tile-uniform.
+template <int T>
+__device__ __forceinline__ void tile_absmax2(double& a, double& b, bool odd) {
+  const unsigned long long ABS = 0x7fffffffffffffffULL;
+  const unsigned long long ua = (unsigned long long)__double_as_longlong(a) & ABS;
+  const unsigned long long ub = (unsigned long long)__double_as_longlong(b) & ABS;
+  const unsigned long long send = odd ? ua : ub;
+  unsigned long long keep = odd ? ub : ua;
+  unsigned long long got = __shfl_xor_sync(FULL_MASK, send, 1);
+  keep = got > keep ? got : keep;
+#pragma unroll
+  for (int o = T / 2; o > 1; o >>= 1) {
+    got = __shfl_xor_sync(FULL_MASK, keep, o);
+    keep = got > keep ? got : keep;
+  }
+  const unsigned long long other = __shfl_xor_sync(FULL_MASK, keep, 1);
+  a = __longlong_as_double((long long)(odd ? other : keep));
+  b = __longlong_as_double((long long)(odd ? keep : other));
+}
+
+// 2^-e for e = exponent of the tile's largest |w_i|: multiplying by it is exact and keeps the
+// un-normalised power iteration inside the double range.  Tile-uniform.
+template <int T>
+__device__ __forceinline__ double tile_pow2_rescale(double w) {
+  unsigned hi = (unsigned)__double2hiint(w) & 0x7fffffffu;
+#pragma unroll
+  for (int o = T / 2; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+  const unsigned e = hi >> 20;
+  const unsigned se = (e == 0u || e >= 2046u) ? 1023u : 2046u - e;
+  return __hiloint2double((int)(se << 20), 0);
+}
+
+struct FwdTile {  // what one lane knows about its problem when the ADMM loop starts
+  double qi, pdiag, radius, rho, tau;
+  const double* Prow;
+  bool valid, vprob, vec32;
+};
+
+// ---- the ADMM loop (Solver.cpp:79-121 / :538-580).  Returns this lane's element of l_2; *it_out = iterations run.
+// Control state is tile-uniform (all lanes of a tile hold identical residuals after the reductions).
+// A finished tile keeps executing the arithmetic with its answer frozen until the whole warp is done.
+template <int T, bool QCQP, bool DENSE>
+__device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t, double* Lb, double* db,
+                                            double* vbuf, int& cur, int lane, int ti, int tile_base, int* it_out) {
+  const int N = p.N;
+  const double mu = p.mu_prox, eps = p.eps;
+  const bool odd = lane & 1;
+  double rho = t.rho, tau_inc = t.tau, tau_dec = t.tau;
+  double mdiag = __dadd_rn(t.pdiag, __dadd_rn(rho, mu));  // P += (rho + mu) I   :75 / :534
+  double irho = 1.0 / rho;
+  double l2 = 0.0, u = 0.0, qprox = t.qi;  // l_2 (== l_2_pred at the top of an iteration), u, q_prox
+  double pinv[T];                          // dense: row ti of (P + (rho+mu) I)^-1 (dead when !DENSE)
+  double pinvd = 0.0;                      // diagonal: its only non-zero entry
+  bool live = t.vprob && p.max_iter > 0;
+  bool refac = true;
+  int rho_up = 0, cpt5 = 0;  // cpt5 = cpt % 5
+  int it = 0, itout = 0;
+  if (!DENSE) {
+    // LLT of a diagonal matrix, then the two substitutions against I:  (1/s) * (1/s),  s = sqrt(m_ii)   :76-77
+    const double a = 1.0 / sqrt(mdiag);
+    pinvd = __dmul_rn(a, a);
+  }
+
+  while (__any_sync(FULL_MASK, live)) {  // warp ballot: leave when every problem of the group has finished
+    if constexpr (DENSE) {
+      // chol = P.llt(); Pinv.setIdentity(); chol.solveInPlace(Pinv)   :76-77, :100-101, :114-115
+      if (__any_sync(FULL_MASK, refac)) {  // all lanes take part (shuffles inside); unchanged tiles recompute the same bits
+        double a[T];
+        load_row<T>(a, t.Prow, N, t.valid, t.vec32);  // L1/L2-resident re-read keeps the row out of the loop's registers
+#pragma unroll
+        for (int j = 0; j < T; j++) {
+          if (j == ti) a[j] = mdiag;
+          else if (j > ti) a[j] = 0.0;
+        }
+        tile_spd_inverse<T>(a, pinv, Lb, db, N, ti, tile_base);
+        refac = false;
+      }
+    }
+
+    // l = Pinv (rho l_2 - u - q_prox)   :80
+    const double rhs = __dsub_rn(__dsub_rn(__dmul_rn(rho, l2), u), qprox);
+    double l;
+    if constexpr (DENSE) {
+      double* vb = vbuf + cur * 32;
+      vb[lane] = t.valid ? rhs : 0.0;
+      __syncwarp();
+      cur ^= 1;
+      l = row_dot<T>(pinv, vb + tile_base, N);
+    } else {
+      l = __dmul_rn(pinvd, rhs);
+    }
+    qprox = __dsub_rn(t.qi, __dmul_rn(mu, l));                                // :81
+    const double relax = __dadd_rn(__dmul_rn(1.5, l), __dmul_rn(-0.5, l2));   // alpha l + (1-alpha) l_2_pred
+    const double z = __dadd_rn(relax, div_by(u, rho, irho));                  // :82   ... + u/rho
+    double l2n;
+    if (!QCQP) {
+      l2n = z < 0 ? 0.0 : z;  // cwiseMax(0)
+    } else {                  // prox_circle :505-519
+      const double zo = __shfl_xor_sync(FULL_MASK, z, 1);
+      const double a0 = odd ? zo : z, a1 = odd ? z : zo;
+      const double nrm = sqrt(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)));
+      l2n = (nrm > t.radius) ? __dmul_rn(z, t.radius) / nrm : z;
+    }
+    const double du = __dsub_rn(relax, l2n);
+    u = __dadd_rn(u, __dmul_rn(rho, du));  // :83
+    // residuals :84-86 / :544-546.  fl(rho x) is monotone in x >= 0, so max_i |rho dl_i| == rho max_i |dl_i|.
+    double rd = __dsub_rn(l2n, l2), rp = du;
+    tile_absmax2<T>(rd, rp, odd);
+    rd = __dmul_rn(rho, rd);
+    ++it;
+
+    bool stop = rd < eps;  // :88
+    if (QCQP) {            // :548 also needs |l|_2: reduce it only when some live tile passed the dual test
+      if (__any_sync(FULL_MASK, stop && live)) {
+        const double lnorm = sqrt(tile_sum<T>(__dmul_rn(l, l)));
+        stop = stop && (rp < __dadd_rn(eps, __dmul_rn(1e-4, lnorm)));
+      }
+    }
+    const bool fin = stop || it >= p.max_iter;
+    if (live) {
+      l2 = l2n;  // :87 (a finished tile keeps its answer: :122 / :581 returns l_2)
+      if (fin) itout = it;
+    }
+    // adaptive rho :91-120 / :551-579
+    const bool cnt = live && !fin && p.adaptive && (rp > __dmul_rn(10., rd) || rd > __dmul_rn(10., rp));
+    live = live && !fin;
+    if (cnt) {
+      if (cpt5 == 0) {  // at most one rho update per 5 counted iterations  :93 / :553
+        if (rp > rd) {  // the increase branch (rp > 10 rd)
+          if (rho_up == -1) {
+            tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));
+            if (!QCQP) tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));  // QP decays both :95-96
+          }
+          mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(tau_inc, 1)));  // :98 / :557
+          rho = __dmul_rn(rho, tau_inc);
+          rho_up = 1;
+        } else {        // the decrease branch (rd > 10 rp)
+          if (rho_up == 1) {
+            if (!QCQP) tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));  // :109-110
+            tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));
+          }
+          const double itau = 1. / tau_dec;
+          mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(itau, 1)));  // :112 / :571
+          rho = div_by(rho, tau_dec, itau);                             // rho /= tau_dec
+          rho_up = -1;
+        }
+        irho = 1.0 / rho;
+        if (DENSE) {
+          refac = true;
+        } else {
+          const double a = 1.0 / sqrt(mdiag);
+          pinvd = __dmul_rn(a, a);
+        }
+      }
+      cpt5 = (cpt5 == 4) ? 0 : cpt5 + 1;
+    }
+  }
+  *it_out = itout;
+  return l2;
+}
+
 template <int T, bool QCQP>
-__global__ void __launch_bounds__(32) admm_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 8 : (T == 16 ? 4 : 3)))
+    admm_fwd_kernel(const FwdParams p) {
   constexpr int G = 32 / T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.N;
-  const int nc = N / 2;
-  const int lane = threadIdx.x;
-  const int ti = lane % T;         // element / row owned by this lane
-  const int tp = lane / T;         // problem slot inside the group
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long g = (long long)blockIdx.x * FWD_WARPS + warp;  // this warp's group
+  if (g >= p.n_groups) return;
+  const int ti = lane % T;
+  const int tp = lane / T;
   const int tile_base = tp * T;
+  const long long prob = g * G + tp;
 
-  const size_t szP = ((size_t)G * N * N + 1) & ~(size_t)1;
-  const size_t szQ = ((size_t)G * N + 1) & ~(size_t)1;
-  const size_t szC = QCQP ? (((size_t)G * nc + 1) & ~(size_t)1) : 0;
-  const size_t stage_sz = szP + szQ + 2 * szC;
-  double* smem = reinterpret_cast<double*>(smem_raw);
-  double* Lbuf = smem + 2 * stage_sz;                   // [G][T][T]
-  double* vbuf = Lbuf + 32 * T;                         // [32]
-  double* dinvb = vbuf + 32;                            // [32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dinvb + 32);
+  FwdTile t;
+  t.vprob = prob < p.B;
+  t.valid = t.vprob && ti < N;
+  t.vec32 = (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0;
+  t.Prow = p.P + (prob * N + ti) * N;
 
-  // zero the padded scratch once: entries with an index >= N are never written afterwards
-  for (int i = lane; i < 32 * T + 64; i += 32) Lbuf[i] = 0.0;
-  if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_barrier_init();
+  double* wsm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * FwdSmem<T>::per_warp_doubles;
+  double* Lb = wsm + tp * T * T;               // [T][T] Cholesky factor of this tile
+  double* vbuf = wsm + 32 * T;                 // [2][32] gemv operand, double-buffered
+  double* db = wsm + 32 * T + 64 + tile_base;  // [T] reciprocal pivots
+
+  // ---- inputs straight into registers
+  double prow[T];
+  load_row<T>(prow, t.Prow, N, t.valid, t.vec32);
+  t.qi = t.valid ? __ldg(p.q + prob * N + ti) : 0.0;
+  t.radius = 0.0;
+  if (QCQP) {
+    const int nc = N >> 1;
+    if (t.valid)  // mul_n = l_n o mu   pybindings.cpp:57
+      t.radius = __dmul_rn(__ldg(p.l_n + prob * nc + (ti >> 1)), __ldg(p.mu + prob * nc + (ti >> 1)));
   }
-  __syncwarp();
+  t.pdiag = 1.0;
+  bool nz = false;
+#pragma unroll
+  for (int j = 0; j < T; j++) {
+    if (j == ti) t.pdiag = t.valid ? prow[j] : 1.0;
+    else nz |= (prow[j] != 0.0);
+  }
+  const bool dense = __any_sync(FULL_MASK, nz);  // warp-uniform: the whole group takes one path
 
-  const long long g_begin = (long long)blockIdx.x * p.groups_per_cta;
-  long long g_end = g_begin + p.groups_per_cta;
-  if (g_end > p.n_groups) g_end = p.n_groups;
-  if (g_begin >= g_end) return;
-
-  uint32_t phase_bits = 0u;    // bit s = parity to wait for on ring slot s
-  uint32_t pending_bits = 0u;  // bit s = a bulk copy is in flight into ring slot s
-
-  // ---- stage-in of group g into ring slot s (all lanes call; lane 0 issues the bulk copies)
-  auto stage_in = [&](long long g, int s) {
-    double* sP = smem + (size_t)s * stage_sz;
-    double* sQ = sP + szP;
-    double* sL = sQ + szQ;
-    double* sM = sL + szC;
-    const long long p0 = g * G;
-    long long rem = p.B - p0;
-    const int np = rem < G ? (int)rem : G;
-    const double* gP = p.P + p0 * N * N;
-    const double* gQ = p.q + p0 * N;
-    const size_t bP = (size_t)np * N * N * 8, bQ = (size_t)np * N * 8, bC = (size_t)np * nc * 8;
-    const bool eP = bulk_eligible(gP, sP, bP), eQ = bulk_eligible(gQ, sQ, bQ);
-    bool eL = false, eM = false;
-    const double* gL = nullptr;
-    const double* gM = nullptr;
-    if (QCQP) {
-      gL = p.l_n + p0 * nc;
-      gM = p.mu + p0 * nc;
-      eL = bulk_eligible(gL, sL, bC);
-      eM = bulk_eligible(gM, sM, bC);
-    }
-    const uint32_t tx = (eP ? (uint32_t)bP : 0u) + (eQ ? (uint32_t)bQ : 0u) + (eL ? (uint32_t)bC : 0u) +
-                        (eM ? (uint32_t)bC : 0u);
-    if (tx) {
-      if (lane == 0) {
-        fence_proxy_async();  // order this warp's earlier generic reads of the slot before the async writes
-        mbar_expect_tx(&bars[s], tx);
-        if (eP) bulk_g2s(sP, gP, (uint32_t)bP, &bars[s]);
-        if (eQ) bulk_g2s(sQ, gQ, (uint32_t)bQ, &bars[s]);
-        if (eL) bulk_g2s(sL, gL, (uint32_t)bC, &bars[s]);
-        if (eM) bulk_g2s(sM, gM, (uint32_t)bC, &bars[s]);
-      }
-      pending_bits |= 1u << s;
-    }
-    if (!eP) warp_copy(sP, gP, np * N * N, lane);
-    if (!eQ) warp_copy(sQ, gQ, np * N, lane);
-    if (QCQP) {
-      if (!eL) warp_copy(sL, gL, np * nc, lane);
-      if (!eM) warp_copy(sM, gM, np * nc, lane);
-    }
+  int cur = 0;  // gemv double buffer: one __syncwarp per product (writes of step k+2 are fenced by step k+1's)
+  if (dense) {  // zero the padded scratch once; entries with an index >= N are never written afterwards
+    for (int i = lane; i < FwdSmem<T>::per_warp_doubles; i += 32) wsm[i] = 0.0;
+    __syncwarp();
+  }
+  auto matvec = [&](double v) -> double {
+    if (!dense) return __dmul_rn(t.pdiag, v);
+    double* vb = vbuf + cur * 32;
+    vb[lane] = v;
+    __syncwarp();
+    cur ^= 1;
+    return row_dot<T>(prow, vb + tile_base, N);
   };
 
-  stage_in(g_begin, 0);
-
-  const double alpha = 1.5;  // alpha_relax  Solver.cpp:64,:523
-  const double mu = p.mu_prox;
-  const double eps = p.eps;
-
-  for (long long g = g_begin; g < g_end; ++g) {
-    const int s = (int)((g - g_begin) & 1);
-    __syncwarp();                       // everyone is done reading slot s^1 (previous group)
-    if (g + 1 < g_end) stage_in(g + 1, s ^ 1);
-    if (pending_bits & (1u << s)) {
-      mbar_wait(&bars[s], (phase_bits >> s) & 1u);
-      phase_bits ^= 1u << s;
-      pending_bits &= ~(1u << s);
+  // ---- power_iteration (Solver.cpp:46-59): fixed count, 10 for the QP (:71), 100 for the QCQP (:530).
+  // The reference divides by |Pv| after every product; the direction of v does not depend on those
+  // scalings, so here the iterate is only rescaled by an exact power of two every 4th product and
+  // normalised once at the end: L agrees with the reference to rounding.
+  double Lmax;
+  {
+    double w = t.valid ? 1.0 : 0.0;
+    const int K = QCQP ? 100 : 10;
+    for (int k = 0; k < K; k++) {
+      w = matvec(w);
+      if ((k & 3) == 3 || k == K - 1) w = __dmul_rn(w, tile_pow2_rescale<T>(w));
     }
-    __syncwarp();
-
-    const double* sP = smem + (size_t)s * stage_sz;
-    const double* sQ = sP + szP;
-    const double* sL = sQ + szQ;
-    const double* sM = sL + szC;
-    const long long p0 = g * G;
-    const long long prob = p0 + tp;
-    const bool vprob = prob < p.B;
-    const bool valid = vprob && ti < N;
-    const int np = (p.B - p0) < G ? (int)(p.B - p0) : G;
-    const double* Ps = sP + (size_t)tp * N * N;
-    double* Lb = Lbuf + tp * T * T;
-    double* vb = vbuf + tile_base;
-    double* db = dinvb + tile_base;
-
-    // ---- is every problem of this group diagonal?  (warp-uniform fast path, decided from the data)
-    bool nz = false;
-    {
-      const int tot = np * N * N;
-      int r = lane / N, c = lane - r * N;  // position inside the flattened [np*N][N] slab
-      const int dr = 32 / N, dc = 32 - dr * N;
-      for (int idx = lane; idx < tot; idx += 32) {
-        if ((r % N) != c && sP[idx] != 0.0) nz = true;
-        r += dr; c += dc;
-        if (c >= N) { c -= N; r += 1; }
-      }
-    }
-    const bool dense = __any_sync(FULL_MASK, nz);
-
-    const double qi = valid ? sQ[tp * N + ti] : 0.0;
-    const double pdiag = valid ? Ps[ti * N + ti] : 1.0;
-    double radius = 0.0;
-    if (QCQP) radius = valid ? sL[tp * nc + (ti >> 1)] * sM[tp * nc + (ti >> 1)] : 0.0;  // pybindings.cpp:57
-
-    // ---- power_iteration (Solver.cpp:46-59): fixed count, 10 for the QP (:71), 100 for the QCQP (:530)
-    double Lmax;
-    {
-      double prow[T];
-      if (dense) {
-#pragma unroll
-        for (int j = 0; j < T; j++) prow[j] = (valid && j < N) ? Ps[ti * N + j] : 0.0;
-      }
-      auto matvec = [&](double v) -> double {
-        if (!dense) return valid ? pdiag * v : 0.0;
-        vb[ti] = v;
-        __syncwarp();
-        double r = tile_row_dot<T>(prow, vb, N);
-        __syncwarp();
-        return r;
-      };
-      double v = valid ? 1 / sqrt((double)N) : 0.0;
-      double z = tile_sum<T>(v * v);
-      if (z > 0) v = v / sqrt(z);
-      const int K = QCQP ? 100 : 10;
-      for (int k = 0; k < K; k++) {
-        double Av = matvec(v);
-        z = tile_sum<T>(Av * Av);
-        v = Av;
-        if (z > 0) v = v / sqrt(z);
-      }
-      double Av = matvec(v);
-      Lmax = tile_sum<T>(v * Av);
-    }
-
-    // ---- rho / tau initialisation (Solver.cpp:72-73, :531-532).  One pow() per lane: even lanes
-    // evaluate the .4 exponent, odd lanes the .15 exponent, and neighbours swap.
-    const double ratio = Lmax / mu;
-    double pw = pow(ratio, (lane & 1) ? .15 : .4);
-    double pw4 = __shfl_sync(FULL_MASK, pw, lane & ~1);
-    double pw15 = __shfl_sync(FULL_MASK, pw, lane | 1);
-    double rho = sqrt(mu * Lmax) * pw4;
-    double tau_inc = pw15, tau_dec = pw15;
-    double mdiag = pdiag + (rho + mu);  // P += (rho+mu) I   :75
-    double inv_rho = 1.0 / rho;
-
-    double l2 = 0.0, u = 0.0, qprox = qi;  // l_2, u, q_prox; l_2_pred == l_2 at the top of every iteration
-    double pinv[T];
-    double pinvd = 0.0;
-    bool refac = true;
-    bool done = !vprob;
-    int rho_up = 0, cpt5 = 0;  // cpt5 = cpt % 5
-    int it = 0;
-    if (p.max_iter <= 0) {
-      if (valid) p.x[prob * N + ti] = 0.0;
-      if (vprob && ti == 0 && p.iters) p.iters[prob] = 0;
-      done = true;
-    }
-
-    while (true) {
-      const bool active = !done;
-      if (!__any_sync(FULL_MASK, active)) break;  // warp ballot: all problems of the group finished
-
-      if (__any_sync(FULL_MASK, refac && active)) {
-        // chol = P.llt(); Pinv = chol.solve(I)   :76-77, :100-101, :114-115
-        if (dense) {
-          double a[T];
-#pragma unroll
-          for (int j = 0; j < T; j++) a[j] = (valid && j < ti) ? Ps[ti * N + j] : 0.0;
-#pragma unroll
-          for (int j = 0; j < T; j++)
-            if (j == ti) a[j] = mdiag;
-          tile_spd_inverse<T>(a, pinv, Lb, db, N, ti, tile_base);
-        } else {
-          pinvd = 1.0 / mdiag;
-        }
-        refac = false;
-      }
-
-      // l = Pinv (rho l_2 - u - q_prox)   :80
-      const double rhs = rho * l2 - u - qprox;
-      double l;
-      if (dense) {
-        vb[ti] = valid ? rhs : 0.0;
-        __syncwarp();
-        l = tile_row_dot<T>(pinv, vb, N);
-        __syncwarp();
-      } else {
-        l = pinvd * rhs;
-      }
-      qprox = qi - mu * l;                              // :81
-      const double relax = alpha * l + (1 - alpha) * l2;  // alpha l + (1-alpha) l_2_pred
-      double z = relax + u * inv_rho;                   // :82  (u/rho as u * (1/rho))
-      double l2n;
-      if (!QCQP) {
-        l2n = z < 0 ? 0.0 : z;                          // cwiseMax(0)
-      } else {                                          // prox_circle :505-519
-        double zo = __shfl_xor_sync(FULL_MASK, z, 1);
-        double a0 = (lane & 1) ? zo : z, a1 = (lane & 1) ? z : zo;
-        double nrm = sqrt(a0 * a0 + a1 * a1);
-        l2n = (nrm > radius) ? z * radius / nrm : z;
-      }
-      const double du = relax - l2n;
-      u += rho * du;                                    // :83
-      const double dl2 = l2n - l2;
-      double rd = QCQP ? fabs(dl2) : fabs(rho * dl2);   // :84-85 / :544-545
-      double rp = fabs(du);                             // :86
-      tile_max2<T>(rd, rp, lane);
-      if (QCQP) rd *= rho;
-      l2 = l2n;                                         // :87
-      ++it;
-
-      // QCQP stop test needs |l|_2 (:548); reduce it only when some live tile passed the dual test.
-      // The any_sync keeps the shuffles inside tile_sum warp-uniform.
-      const bool cand = active && (rd < eps);
-      double lnorm = 0.0;
-      if (QCQP) {
-        if (__any_sync(FULL_MASK, cand)) lnorm = sqrt(tile_sum<T>(l * l));
-      }
-
-      if (active) {
-        const bool stop = QCQP ? (cand && rp < eps + 1e-4 * lnorm) : cand;  // :88 / :548
-        if (stop || it >= p.max_iter) {
-          done = true;
-          if (valid) p.x[prob * N + ti] = l2;           // :122 / :581
-          if (ti == 0 && p.iters) p.iters[prob] = it;
-        } else if (p.adaptive) {
-          if (rp > 10. * rd) {                          // :92 / :552
-            if (cpt5 == 0) {
-              if (rho_up == -1) {
-                tau_inc = 1 + .8 * (tau_inc - 1);
-                if (!QCQP) tau_dec = 1 + .8 * (tau_dec - 1);
-              }
-              mdiag += rho * (tau_inc - 1);
-              rho *= tau_inc;
-              inv_rho = 1.0 / rho;
-              refac = true;
-              rho_up = 1;
-            }
-            cpt5 = (cpt5 == 4) ? 0 : cpt5 + 1;
-          } else if (rd > 10. * rp) {                   // :106 / :566
-            if (cpt5 == 0) {
-              if (rho_up == 1) {
-                if (!QCQP) tau_inc = 1 + .8 * (tau_inc - 1);
-                tau_dec = 1 + .8 * (tau_dec - 1);
-              }
-              mdiag += rho * (1. / tau_dec - 1);
-              rho /= tau_dec;
-              inv_rho = 1.0 / rho;
-              refac = true;
-              rho_up = -1;
-            }
-            cpt5 = (cpt5 == 4) ? 0 : cpt5 + 1;
-          }
-        }
-      }
-    }
+    const double z = tile_sum<T>(__dmul_rn(w, w));
+    const double v = (z > 0) ? w / sqrt(z) : w;
+    Lmax = tile_sum<T>(__dmul_rn(v, matvec(v)));  // l_max = v . (P v)   :56-57
   }
+
+  // ---- rho / tau initialisation (Solver.cpp:72-73, :531-532).  One pow() per lane: even lanes take
+  // the .4 exponent, odd lanes the .15 exponent, neighbours swap.
+  {
+    const double mu = p.mu_prox;
+    const double pw = pow(Lmax / mu, (lane & 1) ? .15 : .4);
+    const double pw4 = __shfl_sync(FULL_MASK, pw, lane & ~1);
+    t.tau = __shfl_sync(FULL_MASK, pw, lane | 1);
+    t.rho = __dmul_rn(sqrt(__dmul_rn(mu, Lmax)), pw4);
+  }
+
+  int it;
+  const double x = dense ? admm_loop<T, QCQP, true>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it)
+                         : admm_loop<T, QCQP, false>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it);
+  if (t.valid) p.x[prob * N + ti] = x;
+  if (t.vprob && ti == 0 && p.iters) p.iters[prob] = it;
 }
 
 template <int T, bool QCQP>
-static cudaError_t launch_fwd_t(const FwdParams& p, cudaStream_t stream, unsigned grid) {
-  const size_t smem = FwdSmem<T>::total_bytes(p.N, QCQP);
-  cudaError_t e = cudaFuncSetAttribute(admm_fwd_kernel<T, QCQP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) return e;
-  admm_fwd_kernel<T, QCQP><<<grid, 32, smem, stream>>>(p);
+static cudaError_t launch_fwd_t(const FwdParams& p, cudaStream_t stream) {
+  static_assert(FwdSmem<T>::bytes <= 48 * 1024, "forward scratch must fit the default dynamic shared memory limit");
+  const long long grid = (p.n_groups + FWD_WARPS - 1) / FWD_WARPS;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+  admm_fwd_kernel<T, QCQP><<<(unsigned)grid, FWD_WARPS * 32, FwdSmem<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, unsigned grid, cudaStream_t stream) {
+cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, cudaStream_t stream) {
   if (qcqp) {
     switch (T) {
-      case 8: return launch_fwd_t<8, true>(p, stream, grid);
-      case 16: return launch_fwd_t<16, true>(p, stream, grid);
-      default: return launch_fwd_t<32, true>(p, stream, grid);
+      case 8: return launch_fwd_t<8, true>(p, stream);
+      case 16: return launch_fwd_t<16, true>(p, stream);
+      default: return launch_fwd_t<32, true>(p, stream);
     }
   } else {
     switch (T) {
-      case 8: return launch_fwd_t<8, false>(p, stream, grid);
-      case 16: return launch_fwd_t<16, false>(p, stream, grid);
-      default: return launch_fwd_t<32, false>(p, stream, grid);
+      case 8: return launch_fwd_t<8, false>(p, stream);
+      case 16: return launch_fwd_t<16, false>(p, stream);
+      default: return launch_fwd_t<32, false>(p, stream);
     }
   }
 }

@@ -61,10 +61,7 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
   p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.iters = iters;
   p.B = B; p.N = N; p.eps = eps; p.mu_prox = mu_prox; p.max_iter = max_iter; p.adaptive = adaptive ? 1 : 0;
   p.n_groups = (B + G - 1) / G;
-  p.groups_per_cta = pick_groups_per_cta(p.n_groups);
-  const long long grid = (p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta;
-  if (grid > 0x7fffffffLL) return DQ_ERR_BAD_ARG;
-  cudaError_t e = dq::launch_admm_fwd(p, qcqp, T, (unsigned)grid, stream);
+  cudaError_t e = dq::launch_admm_fwd(p, qcqp, T, stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DQ_OK;

@@ -19,8 +19,7 @@ struct FwdParams {
   double mu_prox;
   int max_iter;
   int adaptive;
-  int groups_per_cta;
-  long long n_groups;
+  long long n_groups;  // ceil(B / (32/T)): one warp per group
 };
 
 struct BwdParams {
@@ -43,8 +42,8 @@ struct BwdParams {
 // T = tile width (8, 16 or 32 lanes per problem); a warp carries 32/T problems.
 inline int tile_width(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
 
-size_t fwd_smem_bytes(int T, int N, bool qcqp);
-cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, unsigned grid, cudaStream_t stream);
+size_t fwd_smem_bytes(int T);
+cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, cudaStream_t stream);
 cudaError_t launch_qp_bwd(const BwdParams& p, int T, unsigned grid, cudaStream_t stream);
 cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, unsigned grid, cudaStream_t stream);
 
