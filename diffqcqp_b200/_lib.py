@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiffqcqp_b200.so")
+# DQ_LIB_PATH selects another build of the same library (kernel-tuning experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("DQ_LIB_PATH") or os.path.join(_HERE, "libdiffqcqp_b200.so")
 
 # every symbol include/diffqcqp_b200.h declares (tests check the .so exports each one)
 SYMBOLS = [

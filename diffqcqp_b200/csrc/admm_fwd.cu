@@ -24,7 +24,10 @@
 
 namespace dq {
 
-constexpr int FWD_WARPS = 4;  // warps per CTA (independent; no CTA-level barrier anywhere)
+#ifndef DQ_FWD_WARPS
+#define DQ_FWD_WARPS 4
+#endif
+constexpr int FWD_WARPS = DQ_FWD_WARPS;  // warps per CTA (independent; no CTA-level barrier anywhere)
 
 template <int T>
 struct FwdSmem {
@@ -88,28 +91,17 @@ __device__ __forceinline__ double row_dot(const double (&row)[T], const double* 
   return acc;
 }
 
-// Tile maxima of two non-negative quantities at once (sign bits are dropped, i.e. |a|, |b|).  Non-negative
-// doubles order like their bit patterns, so the reduction runs on 64-bit integers (ALU pipe, no NaN
-// fix-up code): after the first exchange even lanes carry `a`, odd lanes carry `b`, the remaining
-// butterfly stages reduce one value per lane and a final exchange hands both back.  Every lane of the
-// tile ends with bit-identical results, which keeps the per-problem control flow tile-uniform.
+// Tile maximum of |a|.  Non-negative doubles order like their bit patterns, so the butterfly runs on
+// 64-bit integers (ALU pipe, no NaN fix-up code).  Every lane of the tile ends with the same bits.
 template <int T>
-__device__ __forceinline__ void tile_absmax2(double& a, double& b, bool odd) {
-  const unsigned long long ABS = 0x7fffffffffffffffULL;
-  const unsigned long long ua = (unsigned long long)__double_as_longlong(a) & ABS;
-  const unsigned long long ub = (unsigned long long)__double_as_longlong(b) & ABS;
-  const unsigned long long send = odd ? ua : ub;
-  unsigned long long keep = odd ? ub : ua;
-  unsigned long long got = __shfl_xor_sync(FULL_MASK, send, 1);
-  keep = got > keep ? got : keep;
+__device__ __forceinline__ double tile_absmax(double a) {
+  unsigned long long k = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffULL;
 #pragma unroll
-  for (int o = T / 2; o > 1; o >>= 1) {
-    got = __shfl_xor_sync(FULL_MASK, keep, o);
-    keep = got > keep ? got : keep;
+  for (int o = T / 2; o > 0; o >>= 1) {
+    const unsigned long long g = __shfl_xor_sync(FULL_MASK, k, o);
+    k = g > k ? g : k;
   }
-  const unsigned long long other = __shfl_xor_sync(FULL_MASK, keep, 1);
-  a = __longlong_as_double((long long)(odd ? other : keep));
-  b = __longlong_as_double((long long)(odd ? keep : other));
+  return __longlong_as_double((long long)k);
 }
 
 // 2^-e for e = exponent of the tile's largest |w_i|: multiplying by it is exact and keeps the
@@ -131,48 +123,45 @@ struct FwdTile {  // what one lane knows about its problem when the ADMM loop st
 };
 
 // ---- the ADMM loop (Solver.cpp:79-121 / :538-580).  Returns this lane's element of l_2; *it_out = iterations run.
-// Control state is tile-uniform (all lanes of a tile hold identical residuals after the reductions).
-// A finished tile keeps executing the arithmetic with its answer frozen until the whole warp is done.
+//
+// Decisions.  With d_i = rho |l_2 - l_2_pred|_i and p_i = |l_2 - (alpha l + (1-alpha) l_2_pred)|_i the reference
+// compares the maxima  rd = max d_i,  rp = max p_i.  fl(c x) is monotone in x >= 0, so
+//     rd < eps        <=>  all_i  fl(rho |dl_i|) < eps              (one ballot)
+//     rp > 10 rd      <=>  any_i  p_i > fl(10 rd)                   (one ballot)
+//     rd > 10 rp      <=>  all_i  rd > fl(10 p_i)                   (one ballot)
+// exactly; only rd needs a real reduction.  All lanes of a tile see identical ballots, so the
+// per-problem control state (live, cpt, rho_up, rho, tau) stays tile-uniform.
+//
+// Pipelining (diagonal path).  The next iteration's arithmetic does not depend on those decisions unless
+// the tile stops or rho changes, so it is issued BEFORE the decisions of the pending iteration are
+// consumed (one speculative iteration in flight): the FP64 chain of iteration k+1 overlaps the shuffle
+// chain of iteration k.  When rho does change (a few times per solve) the speculative iteration is
+// recomputed with the new rho; when the tile stops it is dropped.  Results are identical to the
+// unpipelined order.  A finished tile keeps executing with its answer frozen until the warp is done.
 template <int T, bool QCQP, bool DENSE>
 __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t, double* Lb, double* db,
                                             double* vbuf, int& cur, int lane, int ti, int tile_base, int* it_out) {
   const int N = p.N;
   const double mu = p.mu_prox, eps = p.eps;
   const bool odd = lane & 1;
+  const unsigned tmask = (T == 32 ? 0xffffffffu : ((1u << T) - 1u)) << tile_base;
   double rho = t.rho, tau_inc = t.tau, tau_dec = t.tau;
   double mdiag = __dadd_rn(t.pdiag, __dadd_rn(rho, mu));  // P += (rho + mu) I   :75 / :534
   double irho = 1.0 / rho;
-  double l2 = 0.0, u = 0.0, qprox = t.qi;  // l_2 (== l_2_pred at the top of an iteration), u, q_prox
-  double pinv[T];                          // dense: row ti of (P + (rho+mu) I)^-1 (dead when !DENSE)
-  double pinvd = 0.0;                      // diagonal: its only non-zero entry
+  double pinv[T];      // dense: row ti of (P + (rho+mu) I)^-1 (dead when !DENSE)
+  double pinvd = 0.0;  // diagonal: its only non-zero entry
   bool live = t.vprob && p.max_iter > 0;
   bool refac = true;
   int rho_up = 0, cpt5 = 0;  // cpt5 = cpt % 5
   int it = 0, itout = 0;
-  if (!DENSE) {
-    // LLT of a diagonal matrix, then the two substitutions against I:  (1/s) * (1/s),  s = sqrt(m_ii)   :76-77
-    const double a = 1.0 / sqrt(mdiag);
-    pinvd = __dmul_rn(a, a);
-  }
+  double ans = 0.0;  // l_2 of the last decided iteration of a live tile; frozen once the tile stops
 
-  while (__any_sync(FULL_MASK, live)) {  // warp ballot: leave when every problem of the group has finished
-    if constexpr (DENSE) {
-      // chol = P.llt(); Pinv.setIdentity(); chol.solveInPlace(Pinv)   :76-77, :100-101, :114-115
-      if (__any_sync(FULL_MASK, refac)) {  // all lanes take part (shuffles inside); unchanged tiles recompute the same bits
-        double a[T];
-        load_row<T>(a, t.Prow, N, t.valid, t.vec32);  // L1/L2-resident re-read keeps the row out of the loop's registers
-#pragma unroll
-        for (int j = 0; j < T; j++) {
-          if (j == ti) a[j] = mdiag;
-          else if (j > ti) a[j] = 0.0;
-        }
-        tile_spd_inverse<T>(a, pinv, Lb, db, N, ti, tile_base);
-        refac = false;
-      }
-    }
-
-    // l = Pinv (rho l_2 - u - q_prox)   :80
-    const double rhs = __dsub_rn(__dsub_rn(__dmul_rn(rho, l2), u), qprox);
+  struct Iter {  // one iteration's results: the new state and what the decisions need
+    double l2, u, qprox, dl, du, l;
+  };
+  // arithmetic of one iteration from state s (s.l2 == l_2_pred); reads rho / irho / Pinv
+  auto step = [&](const Iter& s, Iter& o) {
+    const double rhs = __dsub_rn(__dsub_rn(__dmul_rn(rho, s.l2), s.u), s.qprox);  // l = Pinv (rho l_2 - u - q_prox)  :80
     double l;
     if constexpr (DENSE) {
       double* vb = vbuf + cur * 32;
@@ -183,9 +172,9 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
     } else {
       l = __dmul_rn(pinvd, rhs);
     }
-    qprox = __dsub_rn(t.qi, __dmul_rn(mu, l));                                // :81
-    const double relax = __dadd_rn(__dmul_rn(1.5, l), __dmul_rn(-0.5, l2));   // alpha l + (1-alpha) l_2_pred
-    const double z = __dadd_rn(relax, div_by(u, rho, irho));                  // :82   ... + u/rho
+    o.qprox = __dsub_rn(t.qi, __dmul_rn(mu, l));                                 // :81
+    const double relax = __dadd_rn(__dmul_rn(1.5, l), __dmul_rn(-0.5, s.l2));    // alpha l + (1-alpha) l_2_pred
+    const double z = __dadd_rn(relax, div_by(s.u, rho, irho));                   // :82   ... + u/rho
     double l2n;
     if (!QCQP) {
       l2n = z < 0 ? 0.0 : z;  // cwiseMax(0)
@@ -195,32 +184,56 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
       const double nrm = sqrt(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)));
       l2n = (nrm > t.radius) ? __dmul_rn(z, t.radius) / nrm : z;
     }
-    const double du = __dsub_rn(relax, l2n);
-    u = __dadd_rn(u, __dmul_rn(rho, du));  // :83
-    // residuals :84-86 / :544-546.  fl(rho x) is monotone in x >= 0, so max_i |rho dl_i| == rho max_i |dl_i|.
-    double rd = __dsub_rn(l2n, l2), rp = du;
-    tile_absmax2<T>(rd, rp, odd);
-    rd = __dmul_rn(rho, rd);
+    o.du = __dsub_rn(relax, l2n);                 // l_2 - (alpha l + ...) up to sign  :86
+    o.u = __dadd_rn(s.u, __dmul_rn(rho, o.du));   // :83
+    o.dl = __dsub_rn(l2n, s.l2);                  // :84
+    o.l2 = l2n;
+    o.l = l;
+  };
+  // Pinv for the current mdiag.  Dense: all lanes take part (shuffles inside); tiles whose rho did not
+  // change recompute the same bits.  Diagonal: LLT of a diagonal matrix and the two substitutions
+  // against I give (1/s)(1/s), s = sqrt(m_ii)   :76-77, :100-101, :114-115
+  auto refactor = [&]() {
+    if constexpr (DENSE) {
+      double a[T];
+      load_row<T>(a, t.Prow, N, t.valid, t.vec32);  // L1/L2-resident re-read keeps the row out of the loop's registers
+#pragma unroll
+      for (int j = 0; j < T; j++) {
+        if (j == ti) a[j] = mdiag;
+        else if (j > ti) a[j] = 0.0;
+      }
+      tile_spd_inverse<T>(a, pinv, Lb, db, N, ti, tile_base);
+    } else {
+      const double a = 1.0 / sqrt(mdiag);
+      pinvd = __dmul_rn(a, a);
+    }
+  };
+  // Decide the iteration whose results are in `r`.  Returns true when rho changed for this tile.
+  auto decide = [&](const Iter& r) -> bool {
     ++it;
-
-    bool stop = rd < eps;  // :88
-    if (QCQP) {            // :548 also needs |l|_2: reduce it only when some live tile passed the dual test
+    const double adl = fabs(r.dl), pdu = fabs(r.du);
+    bool stop = (__ballot_sync(FULL_MASK, __dmul_rn(rho, adl) < eps) & tmask) == tmask;  // :88 / :548
+    const double rd = __dmul_rn(rho, tile_absmax<T>(r.dl));
+    if (QCQP) {  // also res_prim < eps + eps_rel |l|_2 (:548); the norm is reduced only when a live tile passed the dual test
       if (__any_sync(FULL_MASK, stop && live)) {
-        const double lnorm = sqrt(tile_sum<T>(__dmul_rn(l, l)));
-        stop = stop && (rp < __dadd_rn(eps, __dmul_rn(1e-4, lnorm)));
+        const double thr = __dadd_rn(eps, __dmul_rn(1e-4, sqrt(tile_sum<T>(__dmul_rn(r.l, r.l)))));
+        const bool prim_ok = (__ballot_sync(FULL_MASK, pdu < thr) & tmask) == tmask;  // evaluated by every lane
+        stop = stop & prim_ok;
       }
     }
-    const bool fin = stop || it >= p.max_iter;
+    const bool inc = (__ballot_sync(FULL_MASK, pdu > __dmul_rn(10., rd)) & tmask) != 0u;       // :92 / :552
+    const bool dec = (__ballot_sync(FULL_MASK, rd > __dmul_rn(10., pdu)) & tmask) == tmask;    // :106 / :566
+    const bool fin = stop | (it >= p.max_iter);
     if (live) {
-      l2 = l2n;  // :87 (a finished tile keeps its answer: :122 / :581 returns l_2)
+      ans = r.l2;  // :87; a finished tile keeps it (:122 / :581 return l_2)
       if (fin) itout = it;
     }
-    // adaptive rho :91-120 / :551-579
-    const bool cnt = live && !fin && p.adaptive && (rp > __dmul_rn(10., rd) || rd > __dmul_rn(10., rp));
-    live = live && !fin;
+    const bool cnt = live & !fin & (p.adaptive != 0) & (inc | dec);  // adaptive rho :91-120 / :551-579
+    live = live & !fin;
+    bool changed = false;
     if (cnt) {
       if (cpt5 == 0) {  // at most one rho update per 5 counted iterations  :93 / :553
-        if (rp > rd) {  // the increase branch (rp > 10 rd)
+        if (inc) {
           if (rho_up == -1) {
             tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));
             if (!QCQP) tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));  // QP decays both :95-96
@@ -228,7 +241,7 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
           mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(tau_inc, 1)));  // :98 / :557
           rho = __dmul_rn(rho, tau_inc);
           rho_up = 1;
-        } else {        // the decrease branch (rd > 10 rp)
+        } else {
           if (rho_up == 1) {
             if (!QCQP) tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));  // :109-110
             tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));
@@ -239,22 +252,52 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
           rho_up = -1;
         }
         irho = 1.0 / rho;
-        if (DENSE) {
-          refac = true;
-        } else {
-          const double a = 1.0 / sqrt(mdiag);
-          pinvd = __dmul_rn(a, a);
-        }
+        changed = true;
       }
       cpt5 = (cpt5 == 4) ? 0 : cpt5 + 1;
     }
+    return changed;
+  };
+
+  Iter A, B;
+  A.l2 = 0.0; A.u = 0.0; A.qprox = t.qi; A.dl = A.du = A.l = 0.0;  // l_2 = u = 0, q_prox = q   :67-74
+  if constexpr (DENSE) {
+    while (__any_sync(FULL_MASK, live)) {  // warp ballot: leave when every problem of the group has finished
+      if (__any_sync(FULL_MASK, refac)) refactor();
+      step(A, B);
+      refac = decide(B);
+      A = B;
+    }
+  } else {
+    refactor();
+    step(A, B);  // iteration 1, undecided
+    // body(P, Q): Q = speculative iteration from P's state; decide P; on a rho change recompute Q
+    auto body = [&](Iter& P, Iter& Q) {
+      step(P, Q);
+      const bool changed = decide(P);
+      if constexpr (QCQP) {  // step shuffles (prox_circle): warp-uniform redo; unchanged tiles recompute the same bits
+        if (__any_sync(FULL_MASK, changed)) {
+          if (changed) refactor();
+          step(P, Q);
+        }
+      } else if (changed) {  // QP: step is lane-local, only the tiles whose rho changed redo it
+        refactor();
+        step(P, Q);
+      }
+    };
+    while (true) {  // ping-pong between the two register sets instead of copying them
+      if (!__any_sync(FULL_MASK, live)) break;
+      body(B, A);
+      if (!__any_sync(FULL_MASK, live)) break;
+      body(A, B);
+    }
   }
   *it_out = itout;
-  return l2;
+  return ans;
 }
 
 template <int T, bool QCQP>
-__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 8 : (T == 16 ? 4 : 3)))
+__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : (T == 16 ? 16 : 12)) / FWD_WARPS)
     admm_fwd_kernel(const FwdParams p) {
   constexpr int G = 32 / T;
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -91,8 +91,7 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
   p.groups_per_cta = pick_groups_per_cta(p.n_groups);
   const long long grid = (p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta;
   if (grid > 0x7fffffffLL) return DQ_ERR_BAD_ARG;
-  cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, (unsigned)grid, stream)
-                       : dq::launch_qp_bwd(p, T, (unsigned)grid, stream);
+  cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, (unsigned)grid, stream) : dq::launch_qp_bwd(p, T, stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DQ_OK;

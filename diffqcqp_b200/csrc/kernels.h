@@ -44,7 +44,7 @@ inline int tile_width(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
 
 size_t fwd_smem_bytes(int T);
 cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, cudaStream_t stream);
-cudaError_t launch_qp_bwd(const BwdParams& p, int T, unsigned grid, cudaStream_t stream);
+cudaError_t launch_qp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, unsigned grid, cudaStream_t stream);
 
 }  // namespace dq
