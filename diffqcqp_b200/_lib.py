@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("DQ_LIB_PATH") or os.path.join(_HERE, "libdiffqcqp_b20
 SYMBOLS = [
     "dq_version", "dq_build_arch", "dq_error_string", "dq_last_cuda_error", "dq_max_n",
     "dq_qp_forward", "dq_qp_backward", "dq_qcqp_forward", "dq_qcqp_backward",
-    "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count",
+    "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release",
 ]
 
 _vp = ctypes.c_void_p

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 
 #include "kernels.h"
 
@@ -98,9 +99,12 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
 }
 
 // ---------------------------------------------------------------- host-buffer path
-// Chunked pipeline over two streams: chunk c's H2D copies, kernels and D2H copies are enqueued on
-// stream c&1, so copies of one chunk overlap the solve of the other.  Device memory comes from the
-// stream-ordered pool (cudaMallocAsync), so repeated calls do not pay cudaMalloc.
+// Chunked pipeline over NS streams: chunk c's H2D copies, kernels and D2H copies are enqueued on stream
+// c % NS, so the copy of one chunk overlaps the solve of another and the read-back of a third (the two
+// copy engines run concurrently with the SMs).  Streams and device staging buffers are created once per
+// device and kept (grow-only), so a call costs no cudaMalloc / stream creation after the first.
+// Full PCIe rate needs page-locked host buffers (cudaHostAlloc / torch pin_memory); pageable memory works
+// but is staged by the driver.
 struct HostJob {
   bool qcqp;
   const double *P, *q, *l_n, *mu, *grad_x;
@@ -111,6 +115,17 @@ struct HostJob {
   int max_iter;
 };
 
+constexpr int NS = 3;
+constexpr int MAX_DEVICES = 64;
+struct HostCtx {
+  bool init = false;
+  cudaStream_t st[NS] = {};
+  char* buf[NS] = {};
+  size_t cap[NS] = {};
+};
+HostCtx g_ctx[MAX_DEVICES];
+std::mutex g_ctx_mutex;
+
 #define DQ_CUDA_TRY(expr)                  \
   do {                                     \
     cudaError_t _e = (expr);               \
@@ -119,6 +134,8 @@ struct HostJob {
       goto done;                           \
     }                                      \
   } while (0)
+
+size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 int solve_host(const HostJob& j, int device) {
   int rc = DQ_OK;
@@ -129,69 +146,102 @@ int solve_host(const HostJob& j, int device) {
   if (!j.P || !j.q || !j.x) return DQ_ERR_BAD_ARG;
   if (j.qcqp && (!j.l_n || !j.mu)) return DQ_ERR_BAD_ARG;
   const bool bwd = j.grad_x != nullptr;
-  int prev_dev = -1;
-  cudaStream_t st[2] = {nullptr, nullptr};
   const int N = j.N, nc = N / 2;
   const long long NN = (long long)N * N;
-  // chunk size: ~8 chunks, at least 4096 problems each
-  long long chunk = (j.B + 7) / 8;
-  if (chunk < 4096) chunk = 4096;
-  if (chunk > j.B) chunk = j.B;
-  chunk = (chunk + 3) & ~3LL;  // keep chunk starts 16-byte aligned for every N
+  int prev_dev = -1;
   {
     cudaError_t e = cudaGetDevice(&prev_dev);
     if (e != cudaSuccess) return cuda_fail(e);
-    if (device >= 0 && device != prev_dev) {
+    if (device < 0) device = prev_dev;
+    if (device >= MAX_DEVICES) return DQ_ERR_BAD_ARG;
+    if (device != prev_dev) {
       e = cudaSetDevice(device);
       if (e != cudaSuccess) return cuda_fail(e);
     }
   }
-  DQ_CUDA_TRY(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
-  DQ_CUDA_TRY(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  HostCtx& c = g_ctx[device];
+  // chunking: ~4 chunks per stream so the pipeline has depth, at least 2048 problems each; chunk starts stay
+  // 32-byte aligned for every N (multiple of 4 problems)
+  long long chunk = (j.B + 4 * NS - 1) / (4 * NS);
+  if (chunk < 2048) chunk = 2048;
+  if (chunk > j.B) chunk = j.B;
+  chunk = (chunk + 3) & ~3LL;
+  // per-chunk device layout
+  const size_t oP = 0, oq = oP + align256(chunk * NN * 8), ox = oq + align256(chunk * N * 8),
+               og = ox + align256(chunk * N * 8), ogP = og + align256(chunk * N * 8),
+               ogq = ogP + align256(chunk * NN * 8), oln = ogq + align256(chunk * N * 8),
+               omu = oln + align256(chunk * (size_t)(nc ? nc : 1) * 8), ogl = omu + align256(chunk * (size_t)(nc ? nc : 1) * 8),
+               ogm = ogl + align256(chunk * (size_t)(nc ? nc : 1) * 8), total = ogm + align256(chunk * (size_t)(nc ? nc : 1) * 8);
+  if (!c.init) {
+    for (int s = 0; s < NS; s++) DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.st[s], cudaStreamNonBlocking));
+    c.init = true;
+  }
+  for (int s = 0; s < NS; s++) {
+    if (c.cap[s] < total) {
+      if (c.buf[s]) DQ_CUDA_TRY(cudaFree(c.buf[s]));
+      c.buf[s] = nullptr;
+      c.cap[s] = 0;
+      DQ_CUDA_TRY(cudaMalloc((void**)&c.buf[s], total));
+      c.cap[s] = total;
+    }
+  }
   for (long long c0 = 0, ci = 0; c0 < j.B; c0 += chunk, ++ci) {
     const long long nb = (j.B - c0) < chunk ? (j.B - c0) : chunk;
-    cudaStream_t s = st[ci & 1];
-    double *dP = nullptr, *dq_ = nullptr, *dx = nullptr, *dln = nullptr, *dmu = nullptr, *dg = nullptr,
-           *dgP = nullptr, *dgq = nullptr, *dgl = nullptr, *dgm = nullptr;
-    DQ_CUDA_TRY(cudaMallocAsync(&dP, nb * NN * 8, s));
-    DQ_CUDA_TRY(cudaMallocAsync(&dq_, nb * N * 8, s));
-    DQ_CUDA_TRY(cudaMallocAsync(&dx, nb * N * 8, s));
+    const int si = (int)(ci % NS);
+    cudaStream_t s = c.st[si];
+    char* d = c.buf[si];
+    double *dP = (double*)(d + oP), *dq_ = (double*)(d + oq), *dx = (double*)(d + ox), *dg = (double*)(d + og),
+           *dgP = (double*)(d + ogP), *dgq = (double*)(d + ogq), *dln = (double*)(d + oln), *dmu = (double*)(d + omu),
+           *dgl = (double*)(d + ogl), *dgm = (double*)(d + ogm);
     DQ_CUDA_TRY(cudaMemcpyAsync(dP, j.P + c0 * NN, nb * NN * 8, cudaMemcpyHostToDevice, s));
     DQ_CUDA_TRY(cudaMemcpyAsync(dq_, j.q + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, s));
     if (j.qcqp) {
-      DQ_CUDA_TRY(cudaMallocAsync(&dln, nb * nc * 8, s));
-      DQ_CUDA_TRY(cudaMallocAsync(&dmu, nb * nc * 8, s));
       DQ_CUDA_TRY(cudaMemcpyAsync(dln, j.l_n + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, s));
       DQ_CUDA_TRY(cudaMemcpyAsync(dmu, j.mu + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, s));
     }
+    if (bwd) DQ_CUDA_TRY(cudaMemcpyAsync(dg, j.grad_x + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, s));
     rc = forward_impl(j.qcqp, dP, dq_, dln, dmu, dx, nullptr, nb, N, j.eps, j.mu_prox, j.max_iter, 1, s);
     if (rc != DQ_OK) goto done;
     DQ_CUDA_TRY(cudaMemcpyAsync(j.x + c0 * N, dx, nb * N * 8, cudaMemcpyDeviceToHost, s));
     if (bwd) {
-      DQ_CUDA_TRY(cudaMallocAsync(&dg, nb * N * 8, s));
-      DQ_CUDA_TRY(cudaMemcpyAsync(dg, j.grad_x + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, s));
-      if (j.grad_P) DQ_CUDA_TRY(cudaMallocAsync(&dgP, nb * NN * 8, s));
-      if (j.grad_q) DQ_CUDA_TRY(cudaMallocAsync(&dgq, nb * N * 8, s));
-      if (j.qcqp && j.grad_l_n) DQ_CUDA_TRY(cudaMallocAsync(&dgl, nb * nc * 8, s));
-      if (j.qcqp && j.grad_mu) DQ_CUDA_TRY(cudaMallocAsync(&dgm, nb * nc * 8, s));
-      rc = backward_impl(j.qcqp, dP, dq_, dln, dmu, dx, dg, dgP, dgq, dgl, dgm, nb, N, s);
+      rc = backward_impl(j.qcqp, dP, dq_, dln, dmu, dx, dg, j.grad_P ? dgP : nullptr, j.grad_q ? dgq : nullptr,
+                         (j.qcqp && j.grad_l_n) ? dgl : nullptr, (j.qcqp && j.grad_mu) ? dgm : nullptr, nb, N, s);
       if (rc != DQ_OK) goto done;
-      if (dgP) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_P + c0 * NN, dgP, nb * NN * 8, cudaMemcpyDeviceToHost, s));
-      if (dgq) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_q + c0 * N, dgq, nb * N * 8, cudaMemcpyDeviceToHost, s));
-      if (dgl) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_l_n + c0 * nc, dgl, nb * nc * 8, cudaMemcpyDeviceToHost, s));
-      if (dgm) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_mu + c0 * nc, dgm, nb * nc * 8, cudaMemcpyDeviceToHost, s));
+      if (j.grad_P) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_P + c0 * NN, dgP, nb * NN * 8, cudaMemcpyDeviceToHost, s));
+      if (j.grad_q) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_q + c0 * N, dgq, nb * N * 8, cudaMemcpyDeviceToHost, s));
+      if (j.qcqp && j.grad_l_n)
+        DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_l_n + c0 * nc, dgl, nb * nc * 8, cudaMemcpyDeviceToHost, s));
+      if (j.qcqp && j.grad_mu)
+        DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_mu + c0 * nc, dgm, nb * nc * 8, cudaMemcpyDeviceToHost, s));
     }
-    double* to_free[] = {dP, dq_, dx, dln, dmu, dg, dgP, dgq, dgl, dgm};
-    for (double* ptr : to_free)
-      if (ptr) DQ_CUDA_TRY(cudaFreeAsync(ptr, s));
   }
-  DQ_CUDA_TRY(cudaStreamSynchronize(st[0]));
-  DQ_CUDA_TRY(cudaStreamSynchronize(st[1]));
 done:
-  if (st[0]) cudaStreamDestroy(st[0]);
-  if (st[1]) cudaStreamDestroy(st[1]);
-  if (prev_dev >= 0 && device >= 0 && device != prev_dev) cudaSetDevice(prev_dev);
+  if (c.init)
+    for (int s = 0; s < NS; s++) {
+      cudaError_t e = cudaStreamSynchronize(c.st[s]);
+      if (e != cudaSuccess && rc == DQ_OK) rc = cuda_fail(e);
+    }
+  if (prev_dev >= 0 && device != prev_dev) cudaSetDevice(prev_dev);
   return rc;
+}
+
+void host_release_all() {
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int dvc = 0; dvc < MAX_DEVICES; dvc++) {
+    HostCtx& c = g_ctx[dvc];
+    if (!c.init) continue;
+    cudaSetDevice(dvc);
+    for (int s = 0; s < NS; s++) {
+      if (c.buf[s]) cudaFree(c.buf[s]);
+      if (c.st[s]) cudaStreamDestroy(c.st[s]);
+      c.buf[s] = nullptr; c.cap[s] = 0; c.st[s] = nullptr;
+    }
+    c.init = false;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 }  // namespace
@@ -203,6 +253,7 @@ const char* dq_build_arch(void) { return "sm_100a"; }
 int dq_max_n(void) { return DQ_MAX_N; }
 int dq_last_cuda_error(void) { return g_last_cuda_error; }
 int64_t dq_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+void dq_host_release(void) { host_release_all(); }
 
 const char* dq_error_string(int code) {
   switch (code) {

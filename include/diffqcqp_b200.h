@@ -16,7 +16,7 @@
  *
  * Device entry points take DEVICE pointers and a CUDA stream (cudaStream_t passed as void*, NULL =
  * legacy default stream); they only enqueue work and never synchronise.  *_host entry points take
- * HOST pointers, stage through pinned buffers and return when the outputs are in host memory.
+ * HOST pointers, pipeline the copies with the solve and return when the outputs are in host memory.
  *
  * Pointers must be 8-byte aligned; 16-byte aligned base pointers enable the bulk-copy (TMA) stage-in
  * (otherwise a slower element-wise stage-in is used, same results).
@@ -85,10 +85,13 @@ int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const 
                      double* grad_l_n, double* grad_mu, int64_t B, int32_t N, void* stream);
 
 /*
- * Host-buffer convenience path (what a caller holding CPU arrays, like the reference's users,
- * calls): copies inputs host->device through pinned staging in chunks that overlap with the
- * solve, runs forward (and, when grad_x != NULL, backward) and copies results back.
- * Outputs that are NULL are skipped.  device < 0 means the current device.
+ * Host-buffer path (what a caller holding CPU arrays, like the reference's users, calls): copies
+ * the inputs host->device in chunks on three streams so that the copy of one chunk overlaps the
+ * solve of another and the read-back of a third, runs forward (and, when grad_x != NULL,
+ * backward) and returns when the outputs are in host memory.  Streams and device staging buffers
+ * persist between calls (dq_host_release frees them).  Page-locked host buffers give the full
+ * PCIe rate; pageable ones work but are staged by the driver.  Outputs that are NULL are
+ * skipped.  device < 0 means the current device.  Calls are serialised per process.
  */
 int dq_qp_solve_host(const double* P, const double* q, double* x, const double* grad_x,
                      double* grad_P, double* grad_q, int64_t B, int32_t N, double eps,
@@ -97,6 +100,9 @@ int dq_qcqp_solve_host(const double* P, const double* q, const double* l_n, cons
                        double* x, const double* grad_x, double* grad_P, double* grad_q,
                        double* grad_l_n, double* grad_mu, int64_t B, int32_t N, double eps,
                        double mu_prox, int32_t max_iter, int32_t device);
+
+/* Frees the streams and device staging buffers the *_solve_host entry points keep between calls. */
+void dq_host_release(void);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t dq_launch_count(void);

@@ -136,9 +136,17 @@ double dq_oracle_power_iteration(const double* A, int n, int max_iter) {
 /* ------------------------------------------------------------ Solver.cpp:15-44 ----------- */
 /* A is m x m row-major.  mu_ir=1e-7, epsilon=1e-10, max_iter=10 are the declaration defaults
  * (Solver.cpp:15); every call site uses them (:189,:670).  Returns iterations executed. */
+/* Test hook (not in the reference): when > 0 the refinement loop runs exactly this many steps and
+ * ignores its stopping rule.  The rule compares a residual made of rounding noise with 1e-10
+ * (SURVEY.md F5/F6), so which iterate the reference returns is itself noise-dependent for the
+ * ill-conditioned QCQP systems; the parity tests use this hook to enumerate the candidates. */
+static int g_ir_force = 0;
+void dq_oracle_set_ir_force(int n) { g_ir_force = n; }
+
 int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, int m) {
   const double mu_ir = 1e-7, epsilon = 1e-10;
   const int max_iter = 10;
+  const int force = g_ir_force;
   if (m == 0) return 0;
   double* Ab = dq_alloc(m);
   double* AA = dq_alloc((size_t)m * m);
@@ -177,7 +185,7 @@ int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, 
       res_pred = res;
       not_improved = 0;
     }
-    if (res < epsilon || not_improved == 2) {
+    if (force > 0 ? (it + 1 >= force) : (res < epsilon || not_improved == 2)) {
       it++;
       break;
     }

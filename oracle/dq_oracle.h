@@ -48,6 +48,8 @@ void dq_oracle_solveDerivativesQCQP(const double* P, const double* q, const doub
 /* Exposed helpers (Solver.cpp:46-59, 15-44) for unit tests. */
 double dq_oracle_power_iteration(const double* A, int n, int max_iter);
 int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, int m);
+/* Test hook: n > 0 forces exactly n refinement steps (stop rule ignored); 0 restores the reference rule. */
+void dq_oracle_set_ir_force(int n);
 
 /* ---- batched entry points: the per-item loops of qcqp.py:22-52,141-181 in one C call ----
  * threads <= 0 means "all OpenMP threads"; threads == 1 is the reference's serial shape.

@@ -77,6 +77,8 @@ def lib():
         L.dq_oracle_qcqp_backward_batch.argtypes = [_dp] * 10 + [ctypes.c_int64, ctypes.c_int,
                                                                  ctypes.c_int]
         L.dq_oracle_max_threads.restype = ctypes.c_int
+        L.dq_oracle_set_ir_force.restype = None
+        L.dq_oracle_set_ir_force.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -91,6 +93,11 @@ def _p(a):
 
 def max_threads() -> int:
     return int(lib().dq_oracle_max_threads())
+
+
+def set_ir_force(n: int) -> None:
+    """Test hook: n > 0 makes iterative_refinement run exactly n steps; 0 restores the reference's stop rule."""
+    lib().dq_oracle_set_ir_force(int(n))
 
 
 # ------------------------------------------------------------------ per-problem (pybindings.cpp)

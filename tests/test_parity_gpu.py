@@ -4,7 +4,10 @@ Bars (BASELINE.json north_star): x* within 10*eps of the reference on identical 
 tolerance is written per test.  Where |x*| is far above 1 (ill-conditioned diagonal P: x = -q/p with
 p ~ 1e-5) "10*eps" is applied relative to |x*|_inf -- an absolute 1e-6 on a value of 4e5 is below what
 two correctly rounded evaluation orders of the same trajectory can agree on -- and the fraction of
-problems outside the plain absolute bar is asserted separately (<= 1e-4) and printed.
+problems outside the plain absolute bar is asserted separately (<= 1e-3) and printed.  That fraction is
+what ONE ulp in the reference's own pow() (libm-dependent) does to its result: replaying the oracle with
+rho nudged by +-1 ulp moves 30 of 65536 cfg2 problems (all with |x| >> 1) past the absolute bar at
+eps=1e-10 and none past the relative one.
 Iteration counts must match the oracle exactly: parity means reproducing the ADMM trajectory.
 """
 import os
@@ -34,7 +37,7 @@ def dev(*ts):
     return [t.cuda() for t in ts]
 
 
-def check_x(x, xo, eps, max_abs_frac=1e-4):
+def check_x(x, xo, eps, max_abs_frac=1e-3):
     x = x.cpu().numpy() if isinstance(x, torch.Tensor) else x
     d = np.abs(x - xo).reshape(x.shape[0], -1).max(1)
     scale = np.maximum(1.0, np.abs(xo).reshape(x.shape[0], -1).max(1))
@@ -165,19 +168,41 @@ def test_qcqp_forward_vs_oracle(dq, wl, oracle, B, N, eps, seed, diag):
 @pytest.mark.parametrize("B,N,seed,diag", [(2048, 8, 30, False), (1024, 16, 31, False), (512, 24, 32, False),
                                             (300, 32, 33, False), (512, 16, 34, True), (100, 6, 35, False)])
 def test_qcqp_backward_vs_oracle(dq, wl, oracle, B, N, seed, diag):
-    """Gradient parity is statistical: the reference's own QCQP backward is ill-conditioned
-    (cond(A^T A + mu I) ~ 1e8), two valid evaluation orders differ by p99 ~1e-2 relative in the
-    worst rows.  Bars: median relative row error <= 1e-8, 90th percentile <= 1e-4, and the Tikhonov system
-    residual of the GPU solution no worse than the oracle's (checked in test_qcqp_backward_residual)."""
+    """QCQP gradients against the oracle, iterate by iterate.
+
+    The reference's iterative_refinement (Solver.cpp:15-44) stops on `res < 1e-10` where res, after the first
+    step, is the rounding noise of a system with cond ~ 1e8: whether it returns iterate 1 or
+    iterate 3 is decided by noise, and the two differ by up to O(1) relative in grad_l_n / grad_mu.  So the
+    bar is: every GPU gradient row matches ONE of the oracle's refinement iterates (forced step counts 1..5,
+    oracle test hook) -- grad_P / grad_q to 1e-6, grad_l_n / grad_mu to 1e-4 (p99 1e-6) -- and the median
+    distance to the oracle's own choice stays <= 1e-8."""
     P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=seed, diag=diag)
-    xo = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, EPS, 1000)
-    go = oracle.qcqp_backward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), xo, g.numpy())
+    a = [t.numpy() for t in (P, q, l_n, mu)]
+    xo = oracle.qcqp_forward(*a, None, EPS, 1000)
+    go = oracle.qcqp_backward(*a, xo, g.numpy())
+    cands = []
+    try:
+        for k in (1, 2, 3, 4, 5):
+            oracle.set_ir_force(k)
+            cands.append(oracle.qcqp_backward(*a, xo, g.numpy()))
+    finally:
+        oracle.set_ir_force(0)
     gg = dq.qcqp_backward(*dev(P, q, l_n, mu), torch.from_numpy(xo).cuda(), g.cuda())
-    for name, a, b in zip(("grad_P", "grad_q", "grad_l_n", "grad_mu"), gg, go):
-        r = rel_rows(a, b)
-        assert np.all(np.isfinite(a.cpu().numpy())), name
-        assert np.median(r) <= 1e-8, (name, np.median(r))
-        assert np.percentile(r, 90) <= 1e-4, (name, np.percentile(r, 90))
+    same_choice = None
+    for i, name in enumerate(("grad_P", "grad_q", "grad_l_n", "grad_mu")):
+        got = gg[i].cpu().numpy()
+        assert np.all(np.isfinite(got)), name
+        r_default = rel_rows(got, go[i])
+        r_all = np.stack([rel_rows(got, c[i]) for c in cands])
+        r_best = r_all.min(0)
+        tol, tol99 = (1e-6, 1e-7) if i < 2 else (1e-4, 1e-6)
+        assert r_best.max() <= tol, (name, r_best.max())
+        assert np.percentile(r_best, 99) <= tol99, (name, np.percentile(r_best, 99))
+        assert np.median(r_default) <= 1e-8, (name, np.median(r_default))
+        if i == 1:
+            same_choice = float((r_default <= 1e-6).mean())
+    print(f"\n[qcqp bwd B={B} N={N}] GPU and oracle stop the refinement at the same iterate for {same_choice:.1%} of problems")
+    assert same_choice >= 0.5
 
 
 def test_qcqp_backward_inactive_contacts_exact(dq, wl, oracle):
