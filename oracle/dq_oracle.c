@@ -1,6 +1,7 @@
 /*
  * dq_oracle.c -- CPU restatement of the diffqcqp hot path.  TEST INFRASTRUCTURE ONLY.
- * See dq_oracle.h for the parity status ("parity unpinned") and who may load this.
+ * See dq_oracle.h for the parity status (pinned against oracle/_ref, gap: Eigen's summation
+ * order) and who may load this.
  *
  * Every function cites the reference lines it follows (paths relative to the reference root).
  * Build: -O2/-O3 WITHOUT -march=native / -ffast-math and with -ffp-contract=off, matching the

@@ -4,14 +4,23 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product path (diffqcqp_b200/) never does.
  *
- * PARITY STATUS: "parity unpinned".  The reference (quentinll/diffqcqp) cannot be built in the
- * authoring container: its arithmetic lives in Eigen3 (un-vendored, version unpinned,
- * CMakeLists.txt:11, qcqplib/CMakeLists.txt:5) which is not installed, and the reference ships
- * no golden vectors, no assertions and no expected outputs.  This file
- * restates qcqplib/Solver.cpp, pybindings.cpp and qcqp.py line by line and is pinned only by
- * (i) analytic properties (closed forms, KKT residuals, finite differences) and (ii) a build of
- * the reference's own Solver.cpp against a stand-in linear-algebra header (oracle/_ref, see
- * oracle/Makefile) when /root/reference is present.
+ * PARITY STATUS: pinned against the reference's own source, with one stated gap.
+ *   - The reference ships no golden vectors, assertions or expected outputs,
+ *     and its arithmetic lives in Eigen3 (un-vendored, version unpinned, CMakeLists.txt:11,
+ *     qcqplib/CMakeLists.txt:5), which is not installed here -- so the reference cannot be built
+ *     as shipped.
+ *   - oracle/_ref (`make -C oracle ref`) compiles the reference's UNMODIFIED qcqplib/Solver.cpp from
+ *     where it lies against oracle/eigen_standin/Eigen/Dense, a from-scratch header providing the
+ *     slice of the Eigen API that file uses.  This restatement reproduces that build BIT FOR BIT for
+ *     solveQP, solveDerivativesQP (+dualFromPrimalQP) and solveQCQP, and to a few ulp for
+ *     solveDerivativesQCQP, on seeded batches (tests/test_oracle.py) and on the committed outputs of
+ *     that build (tests/golden/golden_v1.npz, scripts/make_golden.py).  Control flow, constants,
+ *     index bookkeeping, update formulas and evaluation order of Solver.cpp are therefore pinned.
+ *   - THE GAP: Eigen's internal summation order (packetised gemv / dot, blocked LLT for sizes >= 32)
+ *     is not reproduced by the stand-in, which uses plain left-to-right loops.  That is a
+ *     rounding-level difference (SURVEY.md F4 measures its effect on x: <= 1e-14 on dense
+ *     well-conditioned problems; for diagonal P every sum has a single non-zero term, so there the
+ *     stand-in arithmetic is exact and the pin is complete up to libm's pow()).
  *
  * All matrices are row-major, P[i*N+j] == P(i,j) as seen by pybind11's EigenDRef on a C-order
  * numpy array (pybindings.cpp:17).

@@ -3,7 +3,8 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may
 import this module; the product package (diffqcqp_b200/) never does.
 
-Parity status: "parity unpinned" -- see oracle/dq_oracle.h.
+Parity status: pinned bit for bit against the reference's own Solver.cpp built with a stand-in for Eigen
+(oracle/_ref); Eigen's internal summation order is the stated gap -- see oracle/dq_oracle.h.
 
 The functions mirror the reference surface:
   * per-problem: solveQP / solveQCQP / solveDerivativesQP / solveDerivativesQCQP with the argument
