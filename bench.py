@@ -9,9 +9,12 @@ P = diag_embed(rand), q = 2 rand - 1, grad_l = 2 rand - 1, eps=1e-7, max_iter=10
 (launched under torchrun, one rank per GPU) every rank owns its own shard of B problems -- problems
 are independent, so there is no collective on the data path (weak scaling).
 
-Timed region (``value``): inputs resident in HBM, K steps back to back over R rotating input sets
-whose total footprint exceeds the 126 MB L2 (so no step finds its inputs cached from the previous
-use), bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks.
+Timed region (``value``): inputs resident in HBM, K steps over R rotating input sets whose total
+footprint exceeds the 126 MB L2 (so no step finds its inputs cached from the previous use), issued
+round-robin on ``--streams`` CUDA streams (default 2: fwd -> bwd of one batch stay ordered, independent
+batches overlap), bracketed by barrier + synchronize, CUDA events on the launching stream (the side
+streams fork from and join into it), max over ranks.  ``config.single_stream_ms_per_step`` is the same
+loop on one stream.
 ``e2e``: the same metric through the host-buffer C-ABI entry point (dq_qp_solve_host /
 dq_qcqp_solve_host), host->device and device->host copies inside the timed region.
 ``roofline``: the dominant kernel's algorithmic bytes / its measured duration, against the measured
@@ -53,8 +56,10 @@ EPS, MAX_ITER, MU_PROX = 1e-7, 1000, 1e-7
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--streams", type=int, default=2,
+                    help="CUDA streams the timed steps are issued on round-robin (independent batches overlap)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="qp_diag_n8", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override B (per GPU)")
@@ -92,7 +97,8 @@ def hbm_peak():
 
 # ------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    """nvidia-smi polling during the timed region (B200_PROFILING.md's clocks line)."""
+    """SM clock / throttle-reason polling during the timed region (B200_PROFILING.md's clocks line).
+    NVML when importable (1 ms period), else nvidia-smi (one query takes tens of ms)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -100,10 +106,46 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+        self.nvml, self.handle = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                return index
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = []
+        for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                          ("sw_power_cap", 0x4)):
+            flags.append("Active" if (r & bit) else "Not Active")
+        return [str(sm), str(self.max_sm), "0"] + flags
 
     def _run(self):
         while not self.stop_flag.is_set():
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    self.stop_flag.wait(0.001)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
@@ -131,26 +173,28 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------- CPU baseline
-def cpu_run(kind, inp, n, threads=0, use_ref=True):
-    """One forward+backward over the first n problems on the host; returns (seconds, kind, cores)."""
-    import numpy as np
+def cpu_engine(use_ref=True):
+    """The CPU implementation timed as the baseline: the reference's own Solver.cpp build (oracle/_ref,
+    kind "reference") when that library travelled with the repo, else the oracle restatement ("port")."""
     from oracle import pyoracle as orc
 
-    a = {k: np.ascontiguousarray(v[:n].numpy()) for k, v in inp.items()}
-    ref = None
     if use_ref:
         try:
             from oracle import pyref
             if pyref.available():
-                ref = pyref
+                pyref.lib()
+                return pyref, "reference"
         except Exception:
-            ref = None
-    eng = ref if ref is not None else orc
-    cores = eng.max_threads() if threads <= 0 else threads
+            pass
+    return orc, "port"
+
+
+def cpu_pass(eng, kind, a, threads=0):
+    """One forward + backward over the numpy batch `a` on the host cores; returns seconds."""
     t0 = time.perf_counter()
     if kind == "qp":
         x = eng.qp_forward(a["P"], a["q"], None, EPS, MAX_ITER, MU_PROX, threads=threads)
@@ -158,11 +202,28 @@ def cpu_run(kind, inp, n, threads=0, use_ref=True):
     else:
         x = eng.qcqp_forward(a["P"], a["q"], a["l_n"], a["mu"], None, EPS, MAX_ITER, MU_PROX, threads=threads)
         eng.qcqp_backward(a["P"], a["q"], a["l_n"], a["mu"], x, a["g"], threads=threads)
-    dt = time.perf_counter() - t0
-    return dt, ("reference" if ref is not None else "port"), cores
+    return time.perf_counter() - t0
+
+
+def cpu_sample(kind, inp, B, budget_s, sample=0):
+    """Pick a sample of the workload worth about `budget_s` seconds of CPU work: the first n problems, or the
+    whole batch repeated `reps` times when one pass is shorter than the budget."""
+    import numpy as np
+
+    eng, ckind = cpu_engine()
+    n0 = min(B, 4096)
+    a0 = {k: np.ascontiguousarray(v[:n0].numpy()) for k, v in inp.items()}
+    cpu_pass(eng, kind, a0)  # page in the library / thread pool
+    rate = n0 / cpu_pass(eng, kind, a0)
+    n = int(min(B, max(n0, rate * budget_s))) if not sample else min(B, sample)
+    reps = max(1, int(rate * budget_s / n)) if not sample else 1
+    a = {k: np.ascontiguousarray(v[:n].numpy()) for k, v in inp.items()}
+    return eng, ckind, a, n, reps
 
 
 def run_reference_arm(args):
+    """The reference's CPU implementation of the path on this box's host cores, all threads, same workload;
+    each step is a bounded sample sized so that steps + warmup finish within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -170,28 +231,25 @@ def run_reference_arm(args):
     if args.batch:
         B = args.batch
     inp = make_inputs(kind, kw["gen"], B, N, seed=0)
-    # bounded sample: calibrate to ~1.5 s per step so K+W steps stay within minutes
-    n = min(B, 4096)
-    dt, ckind, cores = cpu_run(kind, inp, n)
-    rate = n / dt
-    n = int(min(B, max(4096, rate * 1.5)))
-    if args.cpu_sample:
-        n = min(B, args.cpu_sample)
-    for _ in range(args.warmup):
-        cpu_run(kind, inp, n)
+    budget = min(1.0, 120.0 / max(1, args.steps + args.warmup))  # seconds of CPU work per step
+    eng, ckind, a, n, reps = cpu_sample(kind, inp, B, budget, args.cpu_sample)
+    cores = eng.max_threads()
+    for _ in range(min(args.warmup, 3)):
+        cpu_pass(eng, kind, a)
     ts = []
     for _ in range(args.steps):
-        ts.append(cpu_run(kind, inp, n)[0])
+        ts.append(sum(cpu_pass(eng, kind, a) for _ in range(reps)))
     total = sum(ts)
-    value = n * args.steps / total
+    value = n * reps * args.steps / total
+    sample = (f"each step = {reps} x (fwd+bwd over the first {n} of {B} problems), OpenMP over problems, "
+              f"{'oracle/_ref: the reference Solver.cpp build' if ckind == 'reference' else 'oracle port'}")
     line = {
         "impl": "reference", "metric": "QP/QCQP fwd+bwd solves/sec", "value": value, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "name": args.workload, "B": B, "N": N, "eps": EPS, "max_iter": MAX_ITER,
-                   "step": f"fwd+bwd over the first {n} of {B} problems (bounded sample)"},
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": ckind,
-                         "sample": f"first {n} of {B} problems per step, OpenMP over problems"},
+                   "step": sample},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": ckind, "sample": sample},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,7 +300,7 @@ def run_b200_arm(args):
             d["gm"] = torch.empty((B, nc, 1), dtype=torch.float64, device=dev)
         sets.append(d)
     stream = torch.cuda.current_stream(dev)
-    sp = stream.cuda_stream
+    sp = stream.cuda_stream  # the stream fwd()/bwd() launch on (step_on switches it)
 
     def fwd(d):
         if kind == "qp":
@@ -268,32 +326,62 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- warm-up
-    for w in range(max(args.warmup, 3)):
-        d = sets[w % R]
+    # ---- streams: step k runs on stream k % S (fwd then bwd of one batch stay ordered on their stream; independent
+    # batches overlap, which hides each forward launch's long-iteration tail behind the next batch's work)
+    S = max(1, min(args.streams, R))
+    streams = [stream] + [torch.cuda.Stream(dev) for _ in range(S - 1)]
+    sps = [st.cuda_stream for st in streams]
+
+    def step_on(k, si):
+        nonlocal sp
+        sp = sps[si]
+        d = sets[k % R]
         fwd(d); bwd(d)
+        sp = sps[0]
+
+    def run_steps(n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(ev0)
+        for k in range(n):
+            step_on(k, k % S)
+        for st in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(st)
+            streams[0].wait_event(e)
+        ev1.record(streams[0])
+        return ev0, ev1
+
+    # ---- warm-up
+    W = max(args.warmup, 3)
+    run_steps(W)
     barrier()
 
-    # ---- timed region: exactly K steps, events on the launching stream
+    # ---- timed region: exactly K steps, events on the launching stream (the side streams fork from / join into it)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.005)
     n0 = L.dq_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record(stream)
-    for k in range(args.steps):
-        d = sets[k % R]
-        fwd(d); bwd(d)
-    ev1.record(stream)
+    ev0, ev1 = run_steps(args.steps)
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     launches = int(L.dq_launch_count() - n0)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the same K steps on ONE stream (no overlap between steps): reported next to the headline
+    S_saved, S = S, 1
+    barrier()
+    e0, e1 = run_steps(min(args.steps, 200))
+    barrier()
+    serial_ms_per_step = e0.elapsed_time(e1) / min(args.steps, 200)
+    S = S_saved
+
     # ---- per-kernel durations (separate pass, same rotation, events around each launch)
     fwd_ms, bwd_ms = [], []
-    for k in range(max(args.steps, 10)):
+    for k in range(min(max(args.steps, 10), 100)):
         d = sets[k % R]
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record(stream); fwd(d); e[1].record(stream); bwd(d); e[2].record(stream)
@@ -350,29 +438,36 @@ def run_b200_arm(args):
         dom_bytes = (fb if fwd_avg >= bwd_avg else bb) * B
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         step_achieved = (fb + bb) * B / (total_ms / args.steps * 1e-3) / 1e9
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload, {}).get(dom) if not args.batch else None
+        except Exception:
+            traffic = None
         line = {
             "metric": "QP/QCQP fwd+bwd solves/sec", "value": B * world * args.steps / (total_ms * 1e-3),
-            "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "name": args.workload, "B_per_gpu": B, "N": N, "eps": EPS,
                        "max_iter": MAX_ITER, "sharding": f"batch-sharded x{world}, no data-path collective",
+                       "streams": S, "single_stream_ms_per_step": serial_ms_per_step,
                        "l2_policy": f"{R} rotating input sets, {R * in_bytes_per_set / 1e6:.0f} MB footprint > 126 MB L2"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "alg_bytes_per_solve": {"fwd": fb, "bwd": bb},
                          "kernel_ms": {"fwd": fwd_avg, "bwd": bwd_avg},
-                         "step_achieved_gbs": step_achieved, "step_frac": step_achieved / peak},
+                         "kernel_frac": {"fwd": fb * B / (fwd_avg * 1e-3) / 1e9 / peak, "bwd": bb * B / (bwd_avg * 1e-3) / 1e9 / peak},
+                         "step_achieved_gbs": step_achieved, "step_frac": step_achieved / peak,
+                         "note": "the forward kernel is FP64-issue/latency bound, not HBM bound (DESIGN.md section 6); "
+                                 "kernel_ms are isolated launches on one stream"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world >= 1:
-            n = args.cpu_sample or min(B, 16384)
-            dt, ckind, cores = cpu_run(kind, host0, n)
-            if not args.cpu_sample:  # re-size to about 10 s of CPU work
-                n = int(min(B, max(n, n / dt * 10)))
-                dt, ckind, cores = cpu_run(kind, host0, n)
-            line["cpu_baseline"] = {"value": n / dt, "unit": "solves/s", "cores": cores, "kind": ckind,
-                                    "sample": f"one fwd+bwd over the first {n} of {B} problems, OpenMP over problems, {dt:.2f} s"}
+        if not args.no_cpu_baseline:
+            eng, ckind, a, n, reps = cpu_sample(kind, host0, B, 10.0, args.cpu_sample)
+            dt = sum(cpu_pass(eng, kind, a) for _ in range(reps))
+            line["cpu_baseline"] = {"value": n * reps / dt, "unit": "solves/s", "cores": eng.max_threads(), "kind": ckind,
+                                    "sample": f"{reps} x (fwd+bwd over the first {n} of {B} problems), OpenMP over problems, {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
