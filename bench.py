@@ -193,8 +193,17 @@ def cpu_engine(use_ref=True):
     return orc, "port"
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU legs ask for these explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_pass(eng, kind, a, threads=0):
     """One forward + backward over the numpy batch `a` on the host cores; returns seconds."""
+    threads = threads or host_threads()
     t0 = time.perf_counter()
     if kind == "qp":
         x = eng.qp_forward(a["P"], a["q"], None, EPS, MAX_ITER, MU_PROX, threads=threads)
@@ -233,7 +242,7 @@ def run_reference_arm(args):
     inp = make_inputs(kind, kw["gen"], B, N, seed=0)
     budget = min(1.0, 120.0 / max(1, args.steps + args.warmup))  # seconds of CPU work per step
     eng, ckind, a, n, reps = cpu_sample(kind, inp, B, budget, args.cpu_sample)
-    cores = eng.max_threads()
+    cores = host_threads()
     for _ in range(min(args.warmup, 3)):
         cpu_pass(eng, kind, a)
     ts = []
@@ -466,7 +475,7 @@ def run_b200_arm(args):
         if not args.no_cpu_baseline:
             eng, ckind, a, n, reps = cpu_sample(kind, host0, B, 10.0, args.cpu_sample)
             dt = sum(cpu_pass(eng, kind, a) for _ in range(reps))
-            line["cpu_baseline"] = {"value": n * reps / dt, "unit": "solves/s", "cores": eng.max_threads(), "kind": ckind,
+            line["cpu_baseline"] = {"value": n * reps / dt, "unit": "solves/s", "cores": host_threads(), "kind": ckind,
                                     "sample": f"{reps} x (fwd+bwd over the first {n} of {B} problems), OpenMP over problems, {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     if distributed:

@@ -456,10 +456,17 @@ int dq_oracle_max_threads(void) {
 #endif
 }
 
+/* threads <= 0: OpenMP's default team (honours OMP_NUM_THREADS); threads > 0: that many, capped at the
+ * number of processors (so a launcher that exports OMP_NUM_THREADS=1, like torchrun, can be overridden). */
 static int pick_threads(int threads) {
-  int mx = dq_oracle_max_threads();
-  if (threads <= 0 || threads > mx) return mx;
-  return threads;
+#ifdef _OPENMP
+  if (threads <= 0) return omp_get_max_threads();
+  int np = omp_get_num_procs();
+  return threads > np ? np : threads;
+#else
+  (void)threads;
+  return 1;
+#endif
 }
 
 /* qcqp.py:24-33 (adaptative_rho = True, :27) */

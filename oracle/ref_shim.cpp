@@ -23,10 +23,11 @@ VectorXd to_vec(const double* v, int n) {
   for (int i = 0; i < n; i++) x(i) = v ? v[i] : 0.0;
   return x;
 }
-int pick_threads(int t) {
+int pick_threads(int t) {  // t <= 0: OpenMP default team; t > 0: that many, capped at the processor count
 #ifdef _OPENMP
-  int mx = omp_get_max_threads();
-  return (t <= 0 || t > mx) ? mx : t;
+  if (t <= 0) return omp_get_max_threads();
+  const int np = omp_get_num_procs();
+  return t > np ? np : t;
 #else
   (void)t;
   return 1;
