@@ -73,22 +73,27 @@ __device__ __forceinline__ void load_row(double (&row)[T], const double* __restr
 }
 
 // y_i = sum_j row[j] * vb[j], vb a T-entry shared vector (entries >= N are zero), in chunks of 8 so
-// that N = 24 on a 32-lane tile skips the last quarter.
+// that N = 24 on a 32-lane tile skips the last quarter.  Four interleaved FMA accumulators (j mod 4):
+// a single chain would cost T x 8.2 cycles of FP64 latency per product; Eigen's own gemv accumulates in
+// packets as well, so there is no bit-level order to preserve here.
 template <int T>
 __device__ __forceinline__ double row_dot(const double (&row)[T], const double* vb, int N) {
-  double acc = 0.0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
   for (int j0 = 0; j0 < T; j0 += 8) {
     if (j0 < N) {
 #pragma unroll
-      for (int j = j0; j < j0 + 8; j += 2) {
+      for (int j = j0; j < j0 + 8; j += 4) {
         const double2 v = *reinterpret_cast<const double2*>(vb + j);
-        acc = fma(row[j], v.x, acc);
-        acc = fma(row[j + 1], v.y, acc);
+        const double2 w = *reinterpret_cast<const double2*>(vb + j + 2);
+        a0 = fma(row[j], v.x, a0);
+        a1 = fma(row[j + 1], v.y, a1);
+        a2 = fma(row[j + 2], w.x, a2);
+        a3 = fma(row[j + 3], w.y, a3);
       }
     }
   }
-  return acc;
+  return (a0 + a1) + (a2 + a3);
 }
 
 // Tile maximum of |a|.  Non-negative doubles order like their bit patterns, so the butterfly runs on

@@ -109,6 +109,12 @@ __device__ __forceinline__ void warp_copy(double* dst, const double* __restrict_
 // dinv : this tile's T-entry shared scratch for the reciprocal pivots (entries >= N zero).
 // The factor is stored symmetrically (Lb[i][k] = Lb[k][i] = L(i,k)) so both substitutions read rows,
 // all lanes the same address (shared-memory broadcast), vectorisable to 128-bit loads.
+//
+// Every pivot is applied as a multiplication by 1/sqrt(pivot) (one rsqrt per column, computed by all
+// lanes from the shuffled pivot): a per-lane IEEE division by the pivot costs ~124 cycles of latency and
+// drops into its slow path for the zero numerators of the padded / upper-triangular lanes.  The dot
+// products run on two interleaved FMA accumulators.  Differences from the reference's divide-by-pivot
+// are at rounding level, like Eigen's own blocked evaluation order.
 template <int T>
 __device__ __forceinline__ void tile_spd_inverse(double (&a)[T], double (&out)[T], double* Lb, double* dinv,
                                                  int N, int ti, int tile_base_lane) {
@@ -116,19 +122,23 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[T], double (&out)[T
 #pragma unroll
   for (int k = 0; k < T; k++) {
     if (k < N) {
-      double acc = 0.0;
+      double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-      for (int j = 0; j < k; j++) acc = fma(a[j], Lb[k * T + j], acc);
-      double s = a[k] - acc;
-      double skk = __shfl_sync(FULL_MASK, s, tile_base_lane + k);
-      double piv = sqrt(skk);
-      double val = (ti == k) ? piv : s / piv;
+      for (int j = 0; j + 1 < k; j += 2) {
+        acc0 = fma(a[j], Lb[k * T + j], acc0);
+        acc1 = fma(a[j + 1], Lb[k * T + j + 1], acc1);
+      }
+      if (k & 1) acc0 = fma(a[k - 1], Lb[k * T + k - 1], acc0);
+      const double s = a[k] - (acc0 + acc1);
+      const double skk = __shfl_sync(FULL_MASK, s, tile_base_lane + k);
+      const double rp = rsqrt(skk);                        // 1 / L(k,k)
+      const double val = (ti == k) ? skk * rp : s * rp;    // L(k,k) = sqrt(pivot);  L(i,k) = s / L(k,k)
       a[k] = val;
       if (ti >= k && ti < N) {
         Lb[ti * T + k] = val;
         Lb[k * T + ti] = val;
       }
-      if (ti == k) dinv[k] = 1.0 / piv;
+      if (ti == k) dinv[k] = rp;
       __syncwarp();
     }
   }
@@ -136,10 +146,14 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[T], double (&out)[T
 #pragma unroll
   for (int i = 0; i < T; i++) {
     if (i < N) {
-      double acc = (i == ti) ? 1.0 : 0.0;
+      double acc0 = (i == ti) ? 1.0 : 0.0, acc1 = 0.0;
 #pragma unroll
-      for (int j = 0; j < i; j++) acc = fma(-Lb[i * T + j], out[j], acc);
-      out[i] = acc * dinv[i];
+      for (int j = 0; j + 1 < i; j += 2) {
+        acc0 = fma(-Lb[i * T + j], out[j], acc0);
+        acc1 = fma(-Lb[i * T + j + 1], out[j + 1], acc1);
+      }
+      if (i & 1) acc0 = fma(-Lb[i * T + i - 1], out[i - 1], acc0);
+      out[i] = (acc0 + acc1) * dinv[i];
     } else {
       out[i] = 0.0;
     }
@@ -148,27 +162,35 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[T], double (&out)[T
 #pragma unroll
   for (int i = T - 1; i >= 0; i--) {
     if (i < N) {
-      double acc = 0.0;
+      double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-      for (int j = i + 1; j < T; j++) acc = fma(Lb[i * T + j], out[j], acc);
-      out[i] = (out[i] - acc) * dinv[i];
+      for (int j = i + 1; j + 1 < T; j += 2) {
+        acc0 = fma(Lb[i * T + j], out[j], acc0);
+        acc1 = fma(Lb[i * T + j + 1], out[j + 1], acc1);
+      }
+      if ((T - 1 - i) & 1) acc0 = fma(Lb[i * T + T - 1], out[T - 1], acc0);
+      out[i] = (out[i] - (acc0 + acc1)) * dinv[i];
     }
   }
 }
 
 // y_i = sum_j row[j] * vb[j]  with vb a T-entry shared vector (same for all lanes of the tile).
+// Four interleaved FMA accumulators (j mod 4) instead of one T-long dependent chain.
 template <int T>
 __device__ __forceinline__ double tile_row_dot(const double (&row)[T], const double* vb, int N) {
-  double acc = 0.0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-  for (int j = 0; j < T; j += 2) {
+  for (int j = 0; j < T; j += 4) {
     if (j < N) {
-      double2 v = *reinterpret_cast<const double2*>(vb + j);
-      acc = fma(row[j], v.x, acc);
-      acc = fma(row[j + 1], v.y, acc);
+      const double2 v = *reinterpret_cast<const double2*>(vb + j);
+      const double2 w = *reinterpret_cast<const double2*>(vb + j + 2);
+      a0 = fma(row[j], v.x, a0);
+      a1 = fma(row[j + 1], v.y, a1);
+      a2 = fma(row[j + 2], w.x, a2);
+      a3 = fma(row[j + 3], w.y, a3);
     }
   }
-  return acc;
+  return (a0 + a1) + (a2 + a3);
 }
 
 }  // namespace dq
