@@ -302,7 +302,7 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
 }
 
 template <int T, bool QCQP>
-__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : (T == 16 ? 16 : 12)) / FWD_WARPS)
+__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : 16) / FWD_WARPS)
     admm_fwd_kernel(const FwdParams p) {
   constexpr int G = 32 / T;
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 #include "kernels.h"
@@ -99,12 +100,15 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
 }
 
 // ---------------------------------------------------------------- host-buffer path
-// Chunked pipeline over NS streams: chunk c's H2D copies, kernels and D2H copies are enqueued on stream
-// c % NS, so the copy of one chunk overlaps the solve of another and the read-back of a third (the two
-// copy engines run concurrently with the SMs).  Streams and device staging buffers are created once per
-// device and kept (grow-only), so a call costs no cudaMalloc / stream creation after the first.
-// Full PCIe rate needs page-locked host buffers (cudaHostAlloc / torch pin_memory); pageable memory works
-// but is staged by the driver.
+// Three-stage pipeline over chunks of the batch, one CUDA stream per stage so that no stage ever queues
+// behind another:
+//     in-stream   : H2D copies of chunk c, back to back (keeps the H2D copy engine saturated)
+//     2 compute streams (alternating): forward + backward kernels of chunk c
+//     out-stream  : D2H copy of x (after forward) and of the gradients (after backward)
+// Chunks live in a ring of K device slots; events order the stages (slot filled -> solved -> read back ->
+// free).  Streams, events and slots are created once per device and kept (grow-only), so a call costs no
+// cudaMalloc / stream creation after the first.  Full PCIe rate needs page-locked host buffers
+// (cudaHostAlloc / torch pin_memory); pageable memory works but is staged by the driver.
 struct HostJob {
   bool qcqp;
   const double *P, *q, *l_n, *mu, *grad_x;
@@ -115,13 +119,17 @@ struct HostJob {
   int max_iter;
 };
 
-constexpr int NS = 3;
+constexpr int K_MAX = 16;
 constexpr int MAX_DEVICES = 64;
+int g_slots = 4;   // ring depth (DQ_HOST_SLOTS)
+int g_chunks = 4;  // minimum chunks per call (DQ_HOST_CHUNKS); more when a chunk would exceed ~256 MB of P
+bool g_env_read = false;
 struct HostCtx {
   bool init = false;
-  cudaStream_t st[NS] = {};
-  char* buf[NS] = {};
-  size_t cap[NS] = {};
+  cudaStream_t s_in = nullptr, s_out = nullptr, s_k[2] = {nullptr, nullptr};
+  cudaEvent_t e_in[K_MAX] = {}, e_fwd[K_MAX] = {}, e_bwd[K_MAX] = {}, e_free[K_MAX] = {};
+  char* buf[K_MAX] = {};
+  size_t cap[K_MAX] = {};
 };
 HostCtx g_ctx[MAX_DEVICES];
 std::mutex g_ctx_mutex;
@@ -148,6 +156,7 @@ int solve_host(const HostJob& j, int device) {
   const bool bwd = j.grad_x != nullptr;
   const int N = j.N, nc = N / 2;
   const long long NN = (long long)N * N;
+  const size_t ncs = (size_t)(nc ? nc : 1);
   int prev_dev = -1;
   {
     cudaError_t e = cudaGetDevice(&prev_dev);
@@ -161,23 +170,42 @@ int solve_host(const HostJob& j, int device) {
   }
   std::lock_guard<std::mutex> lock(g_ctx_mutex);
   HostCtx& c = g_ctx[device];
-  // chunking: ~4 chunks per stream so the pipeline has depth, at least 2048 problems each; chunk starts stay
-  // 32-byte aligned for every N (multiple of 4 problems)
-  long long chunk = (j.B + 4 * NS - 1) / (4 * NS);
+  if (!g_env_read) {  // tuning knobs, read once
+    if (const char* e = getenv("DQ_HOST_SLOTS")) { int v = atoi(e); if (v >= 2 && v <= K_MAX) g_slots = v; }
+    if (const char* e = getenv("DQ_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 1024) g_chunks = v; }
+    g_env_read = true;
+  }
+  const int K = g_slots;
+  // chunking: g_chunks chunks, at least 2048 problems each; chunk starts stay 32-byte aligned for every N
+  long long nchunks = g_chunks;
+  {
+    const long long by_size = (j.B * NN * 8 + (256LL << 20) - 1) / (256LL << 20);  // keep a slot's P under ~256 MB
+    if (by_size > nchunks) nchunks = by_size;
+  }
+  long long chunk = (j.B + nchunks - 1) / nchunks;
   if (chunk < 2048) chunk = 2048;
   if (chunk > j.B) chunk = j.B;
   chunk = (chunk + 3) & ~3LL;
-  // per-chunk device layout
+  // per-slot device layout
   const size_t oP = 0, oq = oP + align256(chunk * NN * 8), ox = oq + align256(chunk * N * 8),
                og = ox + align256(chunk * N * 8), ogP = og + align256(chunk * N * 8),
                ogq = ogP + align256(chunk * NN * 8), oln = ogq + align256(chunk * N * 8),
-               omu = oln + align256(chunk * (size_t)(nc ? nc : 1) * 8), ogl = omu + align256(chunk * (size_t)(nc ? nc : 1) * 8),
-               ogm = ogl + align256(chunk * (size_t)(nc ? nc : 1) * 8), total = ogm + align256(chunk * (size_t)(nc ? nc : 1) * 8);
+               omu = oln + align256(chunk * ncs * 8), ogl = omu + align256(chunk * ncs * 8),
+               ogm = ogl + align256(chunk * ncs * 8), total = ogm + align256(chunk * ncs * 8);
   if (!c.init) {
-    for (int s = 0; s < NS; s++) DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.st[s], cudaStreamNonBlocking));
+    DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking));
+    DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking));
+    DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_k[0], cudaStreamNonBlocking));
+    DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_k[1], cudaStreamNonBlocking));
+    for (int s = 0; s < K_MAX; s++) {
+      DQ_CUDA_TRY(cudaEventCreateWithFlags(&c.e_in[s], cudaEventDisableTiming));
+      DQ_CUDA_TRY(cudaEventCreateWithFlags(&c.e_fwd[s], cudaEventDisableTiming));
+      DQ_CUDA_TRY(cudaEventCreateWithFlags(&c.e_bwd[s], cudaEventDisableTiming));
+      DQ_CUDA_TRY(cudaEventCreateWithFlags(&c.e_free[s], cudaEventDisableTiming));
+    }
     c.init = true;
   }
-  for (int s = 0; s < NS; s++) {
+  for (int s = 0; s < K; s++) {
     if (c.cap[s] < total) {
       if (c.buf[s]) DQ_CUDA_TRY(cudaFree(c.buf[s]));
       c.buf[s] = nullptr;
@@ -188,40 +216,56 @@ int solve_host(const HostJob& j, int device) {
   }
   for (long long c0 = 0, ci = 0; c0 < j.B; c0 += chunk, ++ci) {
     const long long nb = (j.B - c0) < chunk ? (j.B - c0) : chunk;
-    const int si = (int)(ci % NS);
-    cudaStream_t s = c.st[si];
+    const int si = (int)(ci % K);
+    cudaStream_t sk = c.s_k[ci & 1];
     char* d = c.buf[si];
     double *dP = (double*)(d + oP), *dq_ = (double*)(d + oq), *dx = (double*)(d + ox), *dg = (double*)(d + og),
            *dgP = (double*)(d + ogP), *dgq = (double*)(d + ogq), *dln = (double*)(d + oln), *dmu = (double*)(d + omu),
            *dgl = (double*)(d + ogl), *dgm = (double*)(d + ogm);
-    DQ_CUDA_TRY(cudaMemcpyAsync(dP, j.P + c0 * NN, nb * NN * 8, cudaMemcpyHostToDevice, s));
-    DQ_CUDA_TRY(cudaMemcpyAsync(dq_, j.q + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, s));
+    // ---- stage 1: inputs in (the slot must have been read back by the chunk that used it K chunks ago)
+    if (ci >= K) DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_in, c.e_free[si], 0));
+    DQ_CUDA_TRY(cudaMemcpyAsync(dP, j.P + c0 * NN, nb * NN * 8, cudaMemcpyHostToDevice, c.s_in));
+    DQ_CUDA_TRY(cudaMemcpyAsync(dq_, j.q + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, c.s_in));
     if (j.qcqp) {
-      DQ_CUDA_TRY(cudaMemcpyAsync(dln, j.l_n + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, s));
-      DQ_CUDA_TRY(cudaMemcpyAsync(dmu, j.mu + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, s));
+      DQ_CUDA_TRY(cudaMemcpyAsync(dln, j.l_n + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, c.s_in));
+      DQ_CUDA_TRY(cudaMemcpyAsync(dmu, j.mu + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, c.s_in));
     }
-    if (bwd) DQ_CUDA_TRY(cudaMemcpyAsync(dg, j.grad_x + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, s));
-    rc = forward_impl(j.qcqp, dP, dq_, dln, dmu, dx, nullptr, nb, N, j.eps, j.mu_prox, j.max_iter, 1, s);
+    if (bwd) DQ_CUDA_TRY(cudaMemcpyAsync(dg, j.grad_x + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, c.s_in));
+    DQ_CUDA_TRY(cudaEventRecord(c.e_in[si], c.s_in));
+    // ---- stage 2: solve
+    DQ_CUDA_TRY(cudaStreamWaitEvent(sk, c.e_in[si], 0));
+    rc = forward_impl(j.qcqp, dP, dq_, dln, dmu, dx, nullptr, nb, N, j.eps, j.mu_prox, j.max_iter, 1, sk);
     if (rc != DQ_OK) goto done;
-    DQ_CUDA_TRY(cudaMemcpyAsync(j.x + c0 * N, dx, nb * N * 8, cudaMemcpyDeviceToHost, s));
+    DQ_CUDA_TRY(cudaEventRecord(c.e_fwd[si], sk));
     if (bwd) {
       rc = backward_impl(j.qcqp, dP, dq_, dln, dmu, dx, dg, j.grad_P ? dgP : nullptr, j.grad_q ? dgq : nullptr,
-                         (j.qcqp && j.grad_l_n) ? dgl : nullptr, (j.qcqp && j.grad_mu) ? dgm : nullptr, nb, N, s);
+                         (j.qcqp && j.grad_l_n) ? dgl : nullptr, (j.qcqp && j.grad_mu) ? dgm : nullptr, nb, N, sk);
       if (rc != DQ_OK) goto done;
-      if (j.grad_P) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_P + c0 * NN, dgP, nb * NN * 8, cudaMemcpyDeviceToHost, s));
-      if (j.grad_q) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_q + c0 * N, dgq, nb * N * 8, cudaMemcpyDeviceToHost, s));
-      if (j.qcqp && j.grad_l_n)
-        DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_l_n + c0 * nc, dgl, nb * nc * 8, cudaMemcpyDeviceToHost, s));
-      if (j.qcqp && j.grad_mu)
-        DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_mu + c0 * nc, dgm, nb * nc * 8, cudaMemcpyDeviceToHost, s));
+      DQ_CUDA_TRY(cudaEventRecord(c.e_bwd[si], sk));
     }
+    // ---- stage 3: results out
+    DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_out, c.e_fwd[si], 0));
+    DQ_CUDA_TRY(cudaMemcpyAsync(j.x + c0 * N, dx, nb * N * 8, cudaMemcpyDeviceToHost, c.s_out));
+    if (bwd) {
+      DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_out, c.e_bwd[si], 0));
+      if (j.grad_P) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_P + c0 * NN, dgP, nb * NN * 8, cudaMemcpyDeviceToHost, c.s_out));
+      if (j.grad_q) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_q + c0 * N, dgq, nb * N * 8, cudaMemcpyDeviceToHost, c.s_out));
+      if (j.qcqp && j.grad_l_n)
+        DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_l_n + c0 * nc, dgl, nb * nc * 8, cudaMemcpyDeviceToHost, c.s_out));
+      if (j.qcqp && j.grad_mu)
+        DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_mu + c0 * nc, dgm, nb * nc * 8, cudaMemcpyDeviceToHost, c.s_out));
+    }
+    DQ_CUDA_TRY(cudaEventRecord(c.e_free[si], c.s_out));
   }
 done:
-  if (c.init)
-    for (int s = 0; s < NS; s++) {
-      cudaError_t e = cudaStreamSynchronize(c.st[s]);
+  if (c.init) {
+    cudaStream_t all[4] = {c.s_in, c.s_k[0], c.s_k[1], c.s_out};
+    for (cudaStream_t st : all) {
+      if (!st) continue;
+      cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess && rc == DQ_OK) rc = cuda_fail(e);
     }
+  }
   if (prev_dev >= 0 && device != prev_dev) cudaSetDevice(prev_dev);
   return rc;
 }
@@ -234,11 +278,18 @@ void host_release_all() {
     HostCtx& c = g_ctx[dvc];
     if (!c.init) continue;
     cudaSetDevice(dvc);
-    for (int s = 0; s < NS; s++) {
+    for (int s = 0; s < K_MAX; s++) {
       if (c.buf[s]) cudaFree(c.buf[s]);
-      if (c.st[s]) cudaStreamDestroy(c.st[s]);
-      c.buf[s] = nullptr; c.cap[s] = 0; c.st[s] = nullptr;
+      c.buf[s] = nullptr; c.cap[s] = 0;
+      if (c.e_in[s]) cudaEventDestroy(c.e_in[s]);
+      if (c.e_fwd[s]) cudaEventDestroy(c.e_fwd[s]);
+      if (c.e_bwd[s]) cudaEventDestroy(c.e_bwd[s]);
+      if (c.e_free[s]) cudaEventDestroy(c.e_free[s]);
+      c.e_in[s] = c.e_fwd[s] = c.e_bwd[s] = c.e_free[s] = nullptr;
     }
+    cudaStream_t all[4] = {c.s_in, c.s_k[0], c.s_k[1], c.s_out};
+    for (cudaStream_t st : all) if (st) cudaStreamDestroy(st);
+    c.s_in = c.s_out = c.s_k[0] = c.s_k[1] = nullptr;
     c.init = false;
   }
   if (prev >= 0) cudaSetDevice(prev);
