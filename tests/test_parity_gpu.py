@@ -320,3 +320,88 @@ def test_launch_counter(dq, wl):
     x = dq.qp_forward(P.cuda(), q.cuda(), EPS, 1000)
     dq.qp_backward(P.cuda(), q.cuda(), x, g.cuda())
     assert launch_count() - n0 == 2
+
+
+# ------------------------------------------------------------------------------------ BASELINE configs 3-5 at full size
+def _kkt_qcqp_residual(P, q, l_n, mu, x):
+    """Stationarity residual of min 1/2 x'Px + q'x s.t. |x_(i)| <= r_i: for interior contacts (Px+q)_(i) = 0, for
+    contacts on the boundary (Px+q)_(i) is anti-parallel to x_(i).  Returns the max violation per problem."""
+    g = torch.bmm(P, x) + q                                  # (B,N,1)
+    B, N = x.shape[0], x.shape[1]
+    g2, x2 = g.view(B, N // 2, 2), x.view(B, N // 2, 2)
+    r = (l_n * mu).view(B, N // 2)
+    nx = x2.norm(dim=2)
+    on_bnd = nx >= r * (1 - 1e-9)
+    # component of g orthogonal to x (boundary) or all of g (interior)
+    xn = x2 / nx.clamp_min(1e-300).unsqueeze(2)
+    g_par = (g2 * xn).sum(2)
+    g_orth = (g2 - g_par.unsqueeze(2) * xn).norm(dim=2)
+    viol = torch.where(on_bnd, torch.maximum(g_orth, g_par.clamp_min(0)), g2.norm(dim=2))
+    return viol.max(1).values
+
+
+def test_cfg3_qcqp_n24_full_size(dq, wl, oracle):
+    """BASELINE configs[2]: B=65536, N=24 QCQP (12 contacts in the reference's N = 2 nc convention).
+    Oracle parity on a 4096-problem prefix; size-independent properties on all 65536."""
+    B, N = 65536, 24
+    P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=3)
+    d = dev(P, q, l_n, mu)
+    x, it = dq.qcqp_forward(*d, EPS, 1000, return_iters=True)
+    n = 4096
+    xo, ito = oracle.qcqp_forward(P[:n].numpy(), q[:n].numpy(), l_n[:n].numpy(), mu[:n].numpy(), None, EPS, 1000, return_iters=True)
+    assert np.array_equal(it[:n].cpu().numpy(), ito)
+    check_x(x[:n], xo, EPS)
+    assert int(it.max()) < 1000 and torch.all(torch.isfinite(x))
+    r = (d[2] * d[3])[:, :, 0]
+    assert torch.all(torch.hypot(x[:, 0::2, 0], x[:, 1::2, 0]) <= r * (1 + 1e-12))           # every contact inside its disk
+    viol = _kkt_qcqp_residual(d[0], d[1], d[2], d[3], x)
+    assert float(viol.max()) <= 5e-3 and float(viol.median()) <= 1e-4                        # early-stopped ADMM (SURVEY F3), not exact KKT
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(2)).cuda()
+    x_perm = dq.qcqp_forward(*[t[perm].contiguous() for t in d], EPS, 1000)
+    assert torch.equal(x_perm, x[perm])                                                     # batch-order independence, bitwise
+    gg = dq.qcqp_backward(*d, x, g.cuda())
+    for t in gg:
+        assert torch.all(torch.isfinite(t))
+    # grad_q = -dl and grad_P = -dl x^T are two views of the same solve
+    assert torch.allclose(gg[0], torch.bmm(gg[1], x.transpose(1, 2)), rtol=1e-14, atol=0)
+
+
+def test_cfg4_mixed_n32_warm_start_is_dead(dq, wl, oracle):
+    """BASELINE configs[3]: N=32 mixed QP/QCQP with warm start from a prior solve (B reduced to 2 x 32768 here; the
+    kernels are size-agnostic).  The reference never reads warm_start: results must not depend on it."""
+    import qcqp
+    B, N = 32768, 32
+    P, q, g = wl.qp_dense(B, N, seed=4)
+    Pd, qd = dev(P, q)
+    x0 = qcqp.QPFn2.apply(Pd, qd + 0.01, torch.zeros_like(qd), EPS, 1000)          # "prior solve"
+    xa = qcqp.QPFn2.apply(Pd, qd, x0, EPS, 1000)                                   # warm-started
+    xb = qcqp.QPFn2.apply(Pd, qd, torch.zeros_like(qd), EPS, 1000)
+    assert torch.equal(xa, xb) and torch.all(xa >= 0)
+    n = 1024
+    xo = oracle.qp_forward(P[:n].numpy(), q[:n].numpy(), x0[:n].cpu().numpy(), EPS, 1000)
+    check_x(xa[:n], xo, EPS)
+    Pq, qq, l_n, mu, g = wl.qcqp_dense(B, N, seed=5)
+    d = dev(Pq, qq, l_n, mu)
+    xa = qcqp.QCQPFn2.apply(*d, torch.randn_like(d[1]), EPS, 1000)
+    xb = qcqp.QCQPFn2.apply(*d, torch.zeros_like(d[1]), EPS, 1000)
+    assert torch.equal(xa, xb)
+    xo = oracle.qcqp_forward(Pq[:n].numpy(), qq[:n].numpy(), l_n[:n].numpy(), mu[:n].numpy(), None, EPS, 1000)
+    check_x(xa[:n], xo, EPS)
+
+
+def test_cfg5_qcqp_n16_per_gpu_shard(dq, wl, oracle):
+    """BASELINE configs[4]: B=2,097,152 N=16 QCQP sharded over 8 GPUs = 262,144 problems per GPU: one rank's shard."""
+    B, N = 262144, 16
+    P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=6)
+    d = dev(P, q, l_n, mu)
+    x, it = dq.qcqp_forward(*d, EPS, 1000, return_iters=True)
+    n = 4096
+    xo, ito = oracle.qcqp_forward(P[-n:].numpy(), q[-n:].numpy(), l_n[-n:].numpy(), mu[-n:].numpy(), None, EPS, 1000, return_iters=True)
+    assert np.array_equal(it[-n:].cpu().numpy(), ito)
+    check_x(x[-n:], xo, EPS)
+    r = (d[2] * d[3])[:, :, 0]
+    assert torch.all(torch.hypot(x[:, 0::2, 0], x[:, 1::2, 0]) <= r * (1 + 1e-12))
+    # a shard solved alone equals the same rows solved inside the full batch (what batch sharding relies on)
+    lo, hi = 3 * B // 8, 4 * B // 8
+    xs = dq.qcqp_forward(*[t[lo:hi].contiguous() for t in d], EPS, 1000)
+    assert torch.equal(xs, x[lo:hi])
