@@ -25,18 +25,6 @@ int cuda_fail(cudaError_t e) {
 
 bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
-// Groups (32/T problems each) per single-warp CTA.  The grid should be several waves of the ~148 SMs x
-// resident-CTA capacity so the hardware CTA scheduler balances the skewed iteration counts, while
-// each CTA still has >= 2 groups when the batch is large so the bulk-copy ring has something to
-// prefetch.
-int pick_groups_per_cta(long long n_groups) {
-  const long long target_ctas = 148LL * 32 * 4;
-  long long k = n_groups / target_ctas;
-  if (k < 1) k = 1;
-  if (k > 8) k = 8;
-  return (int)k;
-}
-
 int check_common(const void* P, const void* q, const void* x, long long B, int N) {
   if (B < 0 || N < 1) return DQ_ERR_BAD_ARG;
   if (N > DQ_MAX_N) return DQ_ERR_UNSUPPORTED_N;
@@ -90,10 +78,7 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
   p.grad_P = grad_P; p.grad_q = grad_q; p.grad_l_n = grad_l_n; p.grad_mu = grad_mu;
   p.B = B; p.N = N;
   p.n_groups = (B + G - 1) / G;
-  p.groups_per_cta = pick_groups_per_cta(p.n_groups);
-  const long long grid = (p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta;
-  if (grid > 0x7fffffffLL) return DQ_ERR_BAD_ARG;
-  cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, (unsigned)grid, stream) : dq::launch_qp_bwd(p, T, stream);
+  cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, stream) : dq::launch_qp_bwd(p, T, stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DQ_OK;

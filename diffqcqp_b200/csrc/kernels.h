@@ -35,8 +35,7 @@ struct BwdParams {
   double* grad_mu;   // nullable, QCQP only
   long long B;
   int N;
-  int groups_per_cta;
-  long long n_groups;
+  long long n_groups;  // ceil(B / (32/T)): one warp per group
 };
 
 // T = tile width (8, 16 or 32 lanes per problem); a warp carries 32/T problems.
@@ -45,6 +44,6 @@ inline int tile_width(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
 size_t fwd_smem_bytes(int T);
 cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, cudaStream_t stream);
 cudaError_t launch_qp_bwd(const BwdParams& p, int T, cudaStream_t stream);
-cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, unsigned grid, cudaStream_t stream);
+cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 
 }  // namespace dq

@@ -24,43 +24,39 @@ namespace dq {
 template <int T>
 struct BwdQcqpSmem {
   static constexpr int WS = T / 2 + 1;  // padded row stride of the L21 scratch
-  __device__ __host__ static size_t stage_doubles(int N) {
-    const int G = 32 / T;
-    size_t p = (size_t)G * N * N, v = (size_t)G * N, c = (size_t)G * (N / 2);
-    return ((p + 1) & ~(size_t)1) + 3 * ((v + 1) & ~(size_t)1) + 2 * ((c + 1) & ~(size_t)1);
-  }
-  __device__ __host__ static size_t scratch_doubles() {
-    // Lbuf 32*T, Dbuf 32*T, Wbuf 32*WS (+pad to even), vbuf 32, dinv 32, cbuf 4*32 (contact broadcast), dlb 32, xb 32
-    return 2 * 32 * T + ((32 * WS + 1) & ~1) + 32 + 32 + 4 * 32 + 32 + 32;
-  }
-  __device__ __host__ static size_t total_bytes(int N) {
-    return (2 * stage_doubles(N) + scratch_doubles()) * sizeof(double) + 2 * sizeof(uint64_t);
-  }
+  static constexpr int WARPS = (T == 8) ? 4 : 2;  // warps per CTA (independent; no CTA-level barrier)
+  // per warp: Lbuf 32*T, Dbuf 32*T, Wbuf 32*WS (+pad to even), vbuf 32, dinv 32, cbuf 4*32 (contact broadcast), dlb 32, xb 32
+  static constexpr int per_warp_doubles = 2 * 32 * T + ((32 * WS + 1) & ~1) + 32 + 32 + 4 * 32 + 32 + 32;
+  static constexpr size_t bytes = (size_t)WARPS * per_warp_doubles * sizeof(double);
 };
 
+#ifndef DQ_QCQP_BWD_MINB32
+#define DQ_QCQP_BWD_MINB32 4
+#endif
 template <int T>
-__global__ void __launch_bounds__(32) qcqp_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP_BWD_MINB32 : (T == 16 ? 6 : 4)))
+    qcqp_bwd_kernel(const BwdParams p) {
   constexpr int G = 32 / T;
   constexpr int T2 = T / 2;
   constexpr int WS = BwdQcqpSmem<T>::WS;
+  constexpr int WARPS = BwdQcqpSmem<T>::WARPS;
   constexpr double MU_IR = 1e-7, EPS_IR = 1e-10;  // Solver.cpp:15
   constexpr double EPS = 1e-10;                   // pybindings.cpp:82 default epsilon
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.N;
   const int nc = N / 2;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long g = (long long)blockIdx.x * WARPS + warp;  // this warp's group of 32/T problems
+  if (g >= p.n_groups) return;
   const int ti = lane % T;
   const int tp = lane / T;
   const int tile_base = tp * T;
   const int c = ti >> 1;          // contact owned by this lane pair
   const bool even = !(lane & 1);
 
-  const size_t szP = ((size_t)G * N * N + 1) & ~(size_t)1;
-  const size_t szV = ((size_t)G * N + 1) & ~(size_t)1;
-  const size_t szC = ((size_t)G * nc + 1) & ~(size_t)1;
-  const size_t stage_sz = szP + 3 * szV + 2 * szC;
-  double* smem = reinterpret_cast<double*>(smem_raw);
-  double* Lbuf = smem + 2 * stage_sz;             // [G][T][T]
+  double* wsm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * BwdQcqpSmem<T>::per_warp_doubles;
+  double* Lbuf = wsm;                             // [G][T][T]
   double* Dbuf = Lbuf + 32 * T;                   // [G][T][T]   D rows, later A22 rows
   double* Wbuf = Dbuf + 32 * T;                   // [32][WS]    L21 rows
   double* vbuf = Wbuf + ((32 * WS + 1) & ~1);     // [32]
@@ -68,94 +64,14 @@ __global__ void __launch_bounds__(32) qcqp_bwd_kernel(const BwdParams p) {
   double* cbuf = dinvb + 32;                      // [4][32]     per-contact broadcast (indexed tile_base/2 + contact)
   double* dlb = cbuf + 4 * 32;                    // [32]
   double* xb = dlb + 32;                          // [32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xb + 32);
-
-  {
-    const int nscratch = (int)BwdQcqpSmem<T>::scratch_doubles();
-    for (int i = lane; i < nscratch; i += 32) Lbuf[i] = 0.0;
-  }
-  if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_barrier_init();
-  }
+  for (int i = lane; i < BwdQcqpSmem<T>::per_warp_doubles; i += 32) wsm[i] = 0.0;  // padded scratch
   __syncwarp();
 
-  const long long g_begin = (long long)blockIdx.x * p.groups_per_cta;
-  long long g_end = g_begin + p.groups_per_cta;
-  if (g_end > p.n_groups) g_end = p.n_groups;
-  if (g_begin >= g_end) return;
-
-  uint32_t phase_bits = 0u, pending_bits = 0u;
-
-  auto stage_in = [&](long long g, int s) {
-    double* sP = smem + (size_t)s * stage_sz;
-    double* sQ = sP + szP;
-    double* sX = sQ + szV;
-    double* sG = sX + szV;
-    double* sL = sG + szV;
-    double* sM = sL + szC;
-    const long long p0 = g * G;
-    const long long rem = p.B - p0;
-    const int np = rem < G ? (int)rem : G;
-    const double* gP = p.P + p0 * N * N;
-    const double* gQ = p.q + p0 * N;
-    const double* gX = p.x + p0 * N;
-    const double* gG = p.grad_x + p0 * N;
-    const double* gL = p.l_n + p0 * nc;
-    const double* gM = p.mu + p0 * nc;
-    const size_t bP = (size_t)np * N * N * 8, bV = (size_t)np * N * 8, bC = (size_t)np * nc * 8;
-    const bool eP = bulk_eligible(gP, sP, bP), eQ = bulk_eligible(gQ, sQ, bV);
-    const bool eX = bulk_eligible(gX, sX, bV), eG = bulk_eligible(gG, sG, bV);
-    const bool eL = bulk_eligible(gL, sL, bC), eM = bulk_eligible(gM, sM, bC);
-    const uint32_t tx = (eP ? (uint32_t)bP : 0u) + (eQ ? (uint32_t)bV : 0u) + (eX ? (uint32_t)bV : 0u) +
-                        (eG ? (uint32_t)bV : 0u) + (eL ? (uint32_t)bC : 0u) + (eM ? (uint32_t)bC : 0u);
-    if (tx) {
-      if (lane == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(&bars[s], tx);
-        if (eP) bulk_g2s(sP, gP, (uint32_t)bP, &bars[s]);
-        if (eQ) bulk_g2s(sQ, gQ, (uint32_t)bV, &bars[s]);
-        if (eX) bulk_g2s(sX, gX, (uint32_t)bV, &bars[s]);
-        if (eG) bulk_g2s(sG, gG, (uint32_t)bV, &bars[s]);
-        if (eL) bulk_g2s(sL, gL, (uint32_t)bC, &bars[s]);
-        if (eM) bulk_g2s(sM, gM, (uint32_t)bC, &bars[s]);
-      }
-      pending_bits |= 1u << s;
-    }
-    if (!eP) warp_copy(sP, gP, np * N * N, lane);
-    if (!eQ) warp_copy(sQ, gQ, np * N, lane);
-    if (!eX) warp_copy(sX, gX, np * N, lane);
-    if (!eG) warp_copy(sG, gG, np * N, lane);
-    if (!eL) warp_copy(sL, gL, np * nc, lane);
-    if (!eM) warp_copy(sM, gM, np * nc, lane);
-  };
-
-  stage_in(g_begin, 0);
-
-  for (long long g = g_begin; g < g_end; ++g) {
-    const int s = (int)((g - g_begin) & 1);
-    __syncwarp();
-    if (g + 1 < g_end) stage_in(g + 1, s ^ 1);
-    if (pending_bits & (1u << s)) {
-      mbar_wait(&bars[s], (phase_bits >> s) & 1u);
-      phase_bits ^= 1u << s;
-      pending_bits &= ~(1u << s);
-    }
-    __syncwarp();
-
-    const double* sP = smem + (size_t)s * stage_sz;
-    const double* sQ = sP + szP;
-    const double* sX = sQ + szV;
-    const double* sG = sX + szV;
-    const double* sL = sG + szV;
-    const double* sM = sL + szC;
+  {
     const long long p0 = g * G;
     const long long prob = p0 + tp;
     const bool vprob = prob < p.B;
     const bool valid = vprob && ti < N;
-    const int np = (p.B - p0) < G ? (int)(p.B - p0) : G;
-    const double* Ps = sP + (size_t)tp * N * N;
     double* Lb = Lbuf + tp * T * T;
     double* Db = Dbuf + tp * T * T;
     double* Wb = Wbuf + tile_base * WS;
@@ -166,16 +82,33 @@ __global__ void __launch_bounds__(32) qcqp_bwd_kernel(const BwdParams p) {
     double* cb2 = cb1 + 32;
     double* cb3 = cb2 + 32;
 
-    const double qi = valid ? sQ[tp * N + ti] : 0.0;
-    const double li = valid ? sX[tp * N + ti] : 0.0;
-    const double gi = valid ? sG[tp * N + ti] : 0.0;
-    const double lnc = valid ? sL[tp * nc + c] : 0.0;
-    const double muc = valid ? sM[tp * nc + c] : 0.0;
+    // ---- inputs straight into registers (rows of P with 256-bit loads when aligned and N == T)
+    const double qi = valid ? __ldg(p.q + prob * N + ti) : 0.0;
+    const double li = valid ? __ldg(p.x + prob * N + ti) : 0.0;
+    const double gi = valid ? __ldg(p.grad_x + prob * N + ti) : 0.0;
+    const double lnc = valid ? __ldg(p.l_n + prob * nc + c) : 0.0;
+    const double muc = valid ? __ldg(p.mu + prob * nc + c) : 0.0;
     const double rc = lnc * muc;  // mul_n  pybindings.cpp:66
 
     double drow[T];  // row ti of P, then of D = P + blkdiag(2 gamma_c I2)
+    {
+      const double* src = p.P + (prob * N + ti) * N;
 #pragma unroll
-    for (int j = 0; j < T; j++) drow[j] = (valid && j < N) ? Ps[ti * N + j] : 0.0;
+      for (int j = 0; j < T; j++) drow[j] = 0.0;
+      if (valid) {
+        if (N == T && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0) {
+#pragma unroll
+          for (int j = 0; j < T; j += 4)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(drow[j]), "=d"(drow[j + 1]), "=d"(drow[j + 2]), "=d"(drow[j + 3])
+                         : "l"(src + j));
+        } else {
+#pragma unroll
+          for (int j = 0; j < T; j++)
+            if (j < N) drow[j] = __ldg(src + j);
+        }
+      }
+    }
 
     // ---- dualFromPrimalQCQP (Solver.cpp:584-617)
     vb[ti] = li;
@@ -344,41 +277,45 @@ __global__ void __launch_bounds__(32) qcqp_bwd_kernel(const BwdParams p) {
       if (even && p.grad_l_n) p.grad_l_n[prob * nc + c] = E2 * dgamma;  // qcqp.py:178
       if (even && p.grad_mu) p.grad_mu[prob * nc + c] = E1 * dgamma;    // qcqp.py:180
     }
-    if (p.grad_P) {  // qcqp.py:174
-      dlb[lane] = dl;
+    if (p.grad_P) {  // qcqp.py:174  grad_P = -dl l^T : lane ti writes row ti
       xb[lane] = li;
       __syncwarp();
-      const int NN = N * N;
-      const int tot = np * NN;
-      double* out = p.grad_P + p0 * NN;
-      int pp = 0, r = lane / N, cidx = lane - r * N;
-      while (r >= N) { r -= N; pp++; }
-      const int dr = 32 / N, dc = 32 - dr * N;
-      for (int idx = lane; idx < tot; idx += 32) {
-        out[idx] = -(dlb[pp * T + r] * xb[pp * T + cidx]);
-        r += dr; cidx += dc;
-        if (cidx >= N) { cidx -= N; r += 1; }
-        while (r >= N) { r -= N; pp++; }
+      if (valid) {
+        double* out = p.grad_P + (prob * N + ti) * N;
+        const double* xr = xb + tile_base;
+        const double ndl = -dl;
+        if (N == T && (reinterpret_cast<uintptr_t>(p.grad_P) & 31u) == 0) {
+#pragma unroll
+          for (int j = 0; j < T; j += 4) {
+            const double2 x01 = *reinterpret_cast<const double2*>(xr + j);
+            const double2 x23 = *reinterpret_cast<const double2*>(xr + j + 2);
+            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(out + j), "d"(ndl * x01.x), "d"(ndl * x01.y),
+                         "d"(ndl * x23.x), "d"(ndl * x23.y)
+                         : "memory");
+          }
+        } else {
+          for (int j = 0; j < N; j++) out[j] = ndl * xr[j];
+        }
       }
-      __syncwarp();
     }
   }
 }
 
 template <int T>
-static cudaError_t launch_qcqp_bwd_t(const BwdParams& p, cudaStream_t stream, unsigned grid) {
-  const size_t smem = BwdQcqpSmem<T>::total_bytes(p.N);
-  cudaError_t e = cudaFuncSetAttribute(qcqp_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  qcqp_bwd_kernel<T><<<grid, 32, smem, stream>>>(p);
+static cudaError_t launch_qcqp_bwd_t(const BwdParams& p, cudaStream_t stream) {
+  static_assert(BwdQcqpSmem<T>::bytes <= 48 * 1024, "backward scratch must fit the default dynamic shared memory limit");
+  constexpr int WARPS = BwdQcqpSmem<T>::WARPS;
+  const long long grid = (p.n_groups + WARPS - 1) / WARPS;
+  if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+  qcqp_bwd_kernel<T><<<(unsigned)grid, WARPS * 32, BwdQcqpSmem<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, unsigned grid, cudaStream_t stream) {
+cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, cudaStream_t stream) {
   switch (T) {
-    case 8: return launch_qcqp_bwd_t<8>(p, stream, grid);
-    case 16: return launch_qcqp_bwd_t<16>(p, stream, grid);
-    default: return launch_qcqp_bwd_t<32>(p, stream, grid);
+    case 8: return launch_qcqp_bwd_t<8>(p, stream);
+    case 16: return launch_qcqp_bwd_t<16>(p, stream);
+    default: return launch_qcqp_bwd_t<32>(p, stream);
   }
 }
 
