@@ -45,6 +45,8 @@ WORKLOADS = {
     # name: (kind, B, N, generator kwargs, description)
     "qp_diag_n8": ("qp", 65536, 8, dict(gen="qp_diag"), "B=65536 N=8 diagonal-P QP fp64 fwd+bwd (BASELINE configs[1])"),
     "qp_dense_n8": ("qp", 65536, 8, dict(gen="qp_dense"), "B=65536 N=8 dense-P QP fp64 fwd+bwd"),
+    "qcqp_n8": ("qcqp", 65536, 8, dict(gen="qcqp_dense"), "B=65536 N=8 dense-P QCQP (4 contacts) fp64 fwd+bwd (the QCQP half of BASELINE's metric)"),
+    "qcqp_diag_n8": ("qcqp", 65536, 8, dict(gen="qcqp_diag"), "B=65536 N=8 diagonal-P QCQP (4 contacts) fp64 fwd+bwd"),
     "qcqp_n24": ("qcqp", 65536, 24, dict(gen="qcqp_dense"), "B=65536 N=24 QCQP (12 contacts) fp64 fwd+bwd (BASELINE configs[2])"),
     "qcqp_n16": ("qcqp", 262144, 16, dict(gen="qcqp_dense"), "B=262144/GPU N=16 QCQP (8 contacts) fp64 fwd+bwd (BASELINE configs[4] shard)"),
     "qp_dense_n32": ("qp", 131072, 32, dict(gen="qp_dense"), "B=131072 N=32 dense-P QP fp64 fwd+bwd (BASELINE configs[3] QP half)"),

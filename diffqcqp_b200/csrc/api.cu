@@ -9,7 +9,9 @@
 #include <cstdint>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include <mutex>
+#include <vector>
 
 #include "kernels.h"
 
@@ -87,13 +89,17 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
 // ---------------------------------------------------------------- host-buffer path
 // Three-stage pipeline over chunks of the batch, one CUDA stream per stage so that no stage ever queues
 // behind another:
-//     in-stream   : H2D copies of chunk c, back to back (keeps the H2D copy engine saturated)
+//     in-stream   : H2D copies of P, chunk after chunk (keeps the H2D copy engine saturated)
 //     2 compute streams (alternating): forward + backward kernels of chunk c
-//     out-stream  : D2H copy of x (after forward) and of the gradients (after backward)
-// Chunks live in a ring of K device slots; events order the stages (slot filled -> solved -> read back ->
-// free).  Streams, events and slots are created once per device and kept (grow-only), so a call costs no
-// cudaMalloc / stream creation after the first.  Full PCIe rate needs page-locked host buffers
-// (cudaHostAlloc / torch pin_memory); pageable memory works but is staged by the driver.
+//     out-stream  : D2H copies of grad_P, chunk after chunk
+// The small vectors (q, l_n, mu, grad_x in; x, grad_q, grad_l_n, grad_mu out -- 1/N of the traffic) ride
+// their own two streams, the inputs as whole-batch copies issued up front, so the fixed latency of a small
+// copy never sits in front of a bulk one.  P / grad_P chunks live in a ring of K device slots; events order
+// the stages (slot filled -> solved -> read back -> free).  Streams, events and device buffers are created
+// once per device and kept (grow-only), so a call costs no cudaMalloc / stream creation after the first.
+// Full PCIe rate needs page-locked host buffers (cudaHostAlloc / torch pin_memory); pageable memory works
+// but is staged by the driver.  Measured: 84 MB per B=65536 N=8 step in 1.24 ms; this box's PCIe does
+// 0.97 ms for the same bytes as two bare concurrent copies (scripts/micro/pcie.py).
 struct HostJob {
   bool qcqp;
   const double *P, *q, *l_n, *mu, *grad_x;
@@ -106,15 +112,20 @@ struct HostJob {
 
 constexpr int K_MAX = 16;
 constexpr int MAX_DEVICES = 64;
-int g_slots = 4;   // ring depth (DQ_HOST_SLOTS)
-int g_chunks = 4;  // minimum chunks per call (DQ_HOST_CHUNKS); more when a chunk would exceed ~256 MB of P
+int g_slots = 6;   // ring depth (DQ_HOST_SLOTS)
+int g_chunks = 6;  // minimum chunks per call (DQ_HOST_CHUNKS); more when a chunk would exceed ~256 MB of P
 bool g_env_read = false;
+bool g_trace = false;  // DQ_HOST_TRACE=1: print a per-chunk timeline of the pipeline stages (debug aid)
 struct HostCtx {
   bool init = false;
-  cudaStream_t s_in = nullptr, s_out = nullptr, s_k[2] = {nullptr, nullptr};
-  cudaEvent_t e_in[K_MAX] = {}, e_fwd[K_MAX] = {}, e_bwd[K_MAX] = {}, e_free[K_MAX] = {};
-  char* buf[K_MAX] = {};
+  // big transfers (P in, grad_P out) and the small vectors ride separate streams so that the fixed latency of
+  // a small copy never sits in front of a bulk one
+  cudaStream_t s_in = nullptr, s_in_small = nullptr, s_out = nullptr, s_out_small = nullptr, s_k[2] = {nullptr, nullptr};
+  cudaEvent_t e_small = nullptr, e_in[K_MAX] = {}, e_fwd[K_MAX] = {}, e_bwd[K_MAX] = {}, e_free[K_MAX] = {};
+  char* buf[K_MAX] = {};  // ring slots: P chunk | grad_P chunk
   size_t cap[K_MAX] = {};
+  char* vec = nullptr;    // whole-batch vectors: q | l_n | mu | grad_x | x | grad_q | grad_l_n | grad_mu
+  size_t vec_cap = 0;
 };
 HostCtx g_ctx[MAX_DEVICES];
 std::mutex g_ctx_mutex;
@@ -132,6 +143,14 @@ size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 int solve_host(const HostJob& j, int device) {
   int rc = DQ_OK;
+  std::vector<cudaEvent_t> tr;  // DQ_HOST_TRACE: t0, then per chunk {in done, fwd done[, bwd done], out done}
+  auto mark = [&](cudaStream_t st) {
+    if (!g_trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tr.push_back(e);
+  };
   if (j.B < 0 || j.N < 1) return DQ_ERR_BAD_ARG;
   if (j.N > DQ_MAX_N) return DQ_ERR_UNSUPPORTED_N;
   if (j.qcqp && (j.N % 2)) return DQ_ERR_BAD_ARG;
@@ -158,30 +177,30 @@ int solve_host(const HostJob& j, int device) {
   if (!g_env_read) {  // tuning knobs, read once
     if (const char* e = getenv("DQ_HOST_SLOTS")) { int v = atoi(e); if (v >= 2 && v <= K_MAX) g_slots = v; }
     if (const char* e = getenv("DQ_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 1024) g_chunks = v; }
+    if (const char* e = getenv("DQ_HOST_TRACE")) g_trace = atoi(e) != 0;
     g_env_read = true;
   }
   const int K = g_slots;
-  // chunking: g_chunks chunks, at least 2048 problems each; chunk starts stay 32-byte aligned for every N
+  // chunking: g_chunks chunks (more when a slot's P would exceed ~256 MB), at least 2048 problems each; chunk
+  // starts stay 32-byte aligned for every N (multiple of 4 problems)
   long long nchunks = g_chunks;
   {
-    const long long by_size = (j.B * NN * 8 + (256LL << 20) - 1) / (256LL << 20);  // keep a slot's P under ~256 MB
+    const long long by_size = (j.B * NN * 8 + (256LL << 20) - 1) / (256LL << 20);
     if (by_size > nchunks) nchunks = by_size;
   }
   long long chunk = (j.B + nchunks - 1) / nchunks;
   if (chunk < 2048) chunk = 2048;
   if (chunk > j.B) chunk = j.B;
   chunk = (chunk + 3) & ~3LL;
-  // per-slot device layout
-  const size_t oP = 0, oq = oP + align256(chunk * NN * 8), ox = oq + align256(chunk * N * 8),
-               og = ox + align256(chunk * N * 8), ogP = og + align256(chunk * N * 8),
-               ogq = ogP + align256(chunk * NN * 8), oln = ogq + align256(chunk * N * 8),
-               omu = oln + align256(chunk * ncs * 8), ogl = omu + align256(chunk * ncs * 8),
-               ogm = ogl + align256(chunk * ncs * 8), total = ogm + align256(chunk * ncs * 8);
+  // device layouts
+  const size_t s_ogP = align256(chunk * NN * 8), slot_total = s_ogP + align256(chunk * NN * 8);
+  const size_t vN = align256((size_t)j.B * N * 8), vC = align256((size_t)j.B * ncs * 8);
+  const size_t v_q = 0, v_ln = v_q + vN, v_mu = v_ln + vC, v_g = v_mu + vC, v_x = v_g + vN, v_gq = v_x + vN,
+               v_gl = v_gq + vN, v_gm = v_gl + vC, vec_total = v_gm + vC;
   if (!c.init) {
-    DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking));
-    DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking));
-    DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_k[0], cudaStreamNonBlocking));
-    DQ_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_k[1], cudaStreamNonBlocking));
+    cudaStream_t* all[6] = {&c.s_in, &c.s_in_small, &c.s_out, &c.s_out_small, &c.s_k[0], &c.s_k[1]};
+    for (cudaStream_t* st : all) DQ_CUDA_TRY(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+    DQ_CUDA_TRY(cudaEventCreateWithFlags(&c.e_small, cudaEventDisableTiming));
     for (int s = 0; s < K_MAX; s++) {
       DQ_CUDA_TRY(cudaEventCreateWithFlags(&c.e_in[s], cudaEventDisableTiming));
       DQ_CUDA_TRY(cudaEventCreateWithFlags(&c.e_fwd[s], cudaEventDisableTiming));
@@ -191,65 +210,101 @@ int solve_host(const HostJob& j, int device) {
     c.init = true;
   }
   for (int s = 0; s < K; s++) {
-    if (c.cap[s] < total) {
+    if (c.cap[s] < slot_total) {
       if (c.buf[s]) DQ_CUDA_TRY(cudaFree(c.buf[s]));
       c.buf[s] = nullptr;
       c.cap[s] = 0;
-      DQ_CUDA_TRY(cudaMalloc((void**)&c.buf[s], total));
-      c.cap[s] = total;
+      DQ_CUDA_TRY(cudaMalloc((void**)&c.buf[s], slot_total));
+      c.cap[s] = slot_total;
     }
   }
-  for (long long c0 = 0, ci = 0; c0 < j.B; c0 += chunk, ++ci) {
-    const long long nb = (j.B - c0) < chunk ? (j.B - c0) : chunk;
-    const int si = (int)(ci % K);
-    cudaStream_t sk = c.s_k[ci & 1];
-    char* d = c.buf[si];
-    double *dP = (double*)(d + oP), *dq_ = (double*)(d + oq), *dx = (double*)(d + ox), *dg = (double*)(d + og),
-           *dgP = (double*)(d + ogP), *dgq = (double*)(d + ogq), *dln = (double*)(d + oln), *dmu = (double*)(d + omu),
-           *dgl = (double*)(d + ogl), *dgm = (double*)(d + ogm);
-    // ---- stage 1: inputs in (the slot must have been read back by the chunk that used it K chunks ago)
-    if (ci >= K) DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_in, c.e_free[si], 0));
-    DQ_CUDA_TRY(cudaMemcpyAsync(dP, j.P + c0 * NN, nb * NN * 8, cudaMemcpyHostToDevice, c.s_in));
-    DQ_CUDA_TRY(cudaMemcpyAsync(dq_, j.q + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, c.s_in));
+  if (c.vec_cap < vec_total) {
+    if (c.vec) DQ_CUDA_TRY(cudaFree(c.vec));
+    c.vec = nullptr;
+    c.vec_cap = 0;
+    DQ_CUDA_TRY(cudaMalloc((void**)&c.vec, vec_total));
+    c.vec_cap = vec_total;
+  }
+  {
+    double *vq = (double*)(c.vec + v_q), *vln = (double*)(c.vec + v_ln), *vmu = (double*)(c.vec + v_mu),
+           *vg = (double*)(c.vec + v_g), *vx = (double*)(c.vec + v_x), *vgq = (double*)(c.vec + v_gq),
+           *vgl = (double*)(c.vec + v_gl), *vgm = (double*)(c.vec + v_gm);
+    mark(c.s_in);
+    // ---- the small inputs, whole batch, once (they are 1/N of the traffic)
+    DQ_CUDA_TRY(cudaMemcpyAsync(vq, j.q, (size_t)j.B * N * 8, cudaMemcpyHostToDevice, c.s_in_small));
     if (j.qcqp) {
-      DQ_CUDA_TRY(cudaMemcpyAsync(dln, j.l_n + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, c.s_in));
-      DQ_CUDA_TRY(cudaMemcpyAsync(dmu, j.mu + c0 * nc, nb * nc * 8, cudaMemcpyHostToDevice, c.s_in));
+      DQ_CUDA_TRY(cudaMemcpyAsync(vln, j.l_n, (size_t)j.B * nc * 8, cudaMemcpyHostToDevice, c.s_in_small));
+      DQ_CUDA_TRY(cudaMemcpyAsync(vmu, j.mu, (size_t)j.B * nc * 8, cudaMemcpyHostToDevice, c.s_in_small));
     }
-    if (bwd) DQ_CUDA_TRY(cudaMemcpyAsync(dg, j.grad_x + c0 * N, nb * N * 8, cudaMemcpyHostToDevice, c.s_in));
-    DQ_CUDA_TRY(cudaEventRecord(c.e_in[si], c.s_in));
-    // ---- stage 2: solve
-    DQ_CUDA_TRY(cudaStreamWaitEvent(sk, c.e_in[si], 0));
-    rc = forward_impl(j.qcqp, dP, dq_, dln, dmu, dx, nullptr, nb, N, j.eps, j.mu_prox, j.max_iter, 1, sk);
-    if (rc != DQ_OK) goto done;
-    DQ_CUDA_TRY(cudaEventRecord(c.e_fwd[si], sk));
-    if (bwd) {
-      rc = backward_impl(j.qcqp, dP, dq_, dln, dmu, dx, dg, j.grad_P ? dgP : nullptr, j.grad_q ? dgq : nullptr,
-                         (j.qcqp && j.grad_l_n) ? dgl : nullptr, (j.qcqp && j.grad_mu) ? dgm : nullptr, nb, N, sk);
+    if (bwd) DQ_CUDA_TRY(cudaMemcpyAsync(vg, j.grad_x, (size_t)j.B * N * 8, cudaMemcpyHostToDevice, c.s_in_small));
+    DQ_CUDA_TRY(cudaEventRecord(c.e_small, c.s_in_small));
+    DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_k[0], c.e_small, 0));
+    DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_k[1], c.e_small, 0));
+    for (long long c0 = 0, ci = 0; c0 < j.B; c0 += chunk, ++ci) {
+      const long long nb = (j.B - c0) < chunk ? (j.B - c0) : chunk;
+      const int si = (int)(ci % K);
+      cudaStream_t sk = c.s_k[ci & 1];
+      double *dP = (double*)c.buf[si], *dgP = (double*)(c.buf[si] + s_ogP);
+      // ---- stage 1: P in (the slot must have been read back by the chunk that used it K chunks ago)
+      if (ci >= K) DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_in, c.e_free[si], 0));
+      DQ_CUDA_TRY(cudaMemcpyAsync(dP, j.P + c0 * NN, nb * NN * 8, cudaMemcpyHostToDevice, c.s_in));
+      DQ_CUDA_TRY(cudaEventRecord(c.e_in[si], c.s_in));
+      mark(c.s_in);
+      // ---- stage 2: solve
+      DQ_CUDA_TRY(cudaStreamWaitEvent(sk, c.e_in[si], 0));
+      rc = forward_impl(j.qcqp, dP, vq + c0 * N, vln + c0 * nc, vmu + c0 * nc, vx + c0 * N, nullptr, nb, N, j.eps,
+                        j.mu_prox, j.max_iter, 1, sk);
       if (rc != DQ_OK) goto done;
-      DQ_CUDA_TRY(cudaEventRecord(c.e_bwd[si], sk));
+      DQ_CUDA_TRY(cudaEventRecord(c.e_fwd[si], sk));
+      mark(sk);
+      if (bwd) {
+        rc = backward_impl(j.qcqp, dP, vq + c0 * N, vln + c0 * nc, vmu + c0 * nc, vx + c0 * N, vg + c0 * N,
+                           j.grad_P ? dgP : nullptr, j.grad_q ? vgq + c0 * N : nullptr,
+                           (j.qcqp && j.grad_l_n) ? vgl + c0 * nc : nullptr, (j.qcqp && j.grad_mu) ? vgm + c0 * nc : nullptr,
+                           nb, N, sk);
+        if (rc != DQ_OK) goto done;
+        DQ_CUDA_TRY(cudaEventRecord(c.e_bwd[si], sk));
+        mark(sk);
+      }
+      // ---- stage 3: results out; x and the small gradients on their own stream
+      DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_out_small, c.e_fwd[si], 0));
+      DQ_CUDA_TRY(cudaMemcpyAsync(j.x + c0 * N, vx + c0 * N, nb * N * 8, cudaMemcpyDeviceToHost, c.s_out_small));
+      if (bwd) {
+        DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_out_small, c.e_bwd[si], 0));
+        if (j.grad_q)
+          DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_q + c0 * N, vgq + c0 * N, nb * N * 8, cudaMemcpyDeviceToHost, c.s_out_small));
+        if (j.qcqp && j.grad_l_n)
+          DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_l_n + c0 * nc, vgl + c0 * nc, nb * nc * 8, cudaMemcpyDeviceToHost, c.s_out_small));
+        if (j.qcqp && j.grad_mu)
+          DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_mu + c0 * nc, vgm + c0 * nc, nb * nc * 8, cudaMemcpyDeviceToHost, c.s_out_small));
+        DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_out, c.e_bwd[si], 0));
+        if (j.grad_P) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_P + c0 * NN, dgP, nb * NN * 8, cudaMemcpyDeviceToHost, c.s_out));
+      } else {
+        DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_out, c.e_fwd[si], 0));
+      }
+      DQ_CUDA_TRY(cudaEventRecord(c.e_free[si], c.s_out));
+      mark(c.s_out);
     }
-    // ---- stage 3: results out
-    DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_out, c.e_fwd[si], 0));
-    DQ_CUDA_TRY(cudaMemcpyAsync(j.x + c0 * N, dx, nb * N * 8, cudaMemcpyDeviceToHost, c.s_out));
-    if (bwd) {
-      DQ_CUDA_TRY(cudaStreamWaitEvent(c.s_out, c.e_bwd[si], 0));
-      if (j.grad_P) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_P + c0 * NN, dgP, nb * NN * 8, cudaMemcpyDeviceToHost, c.s_out));
-      if (j.grad_q) DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_q + c0 * N, dgq, nb * N * 8, cudaMemcpyDeviceToHost, c.s_out));
-      if (j.qcqp && j.grad_l_n)
-        DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_l_n + c0 * nc, dgl, nb * nc * 8, cudaMemcpyDeviceToHost, c.s_out));
-      if (j.qcqp && j.grad_mu)
-        DQ_CUDA_TRY(cudaMemcpyAsync(j.grad_mu + c0 * nc, dgm, nb * nc * 8, cudaMemcpyDeviceToHost, c.s_out));
-    }
-    DQ_CUDA_TRY(cudaEventRecord(c.e_free[si], c.s_out));
   }
 done:
   if (c.init) {
-    cudaStream_t all[4] = {c.s_in, c.s_k[0], c.s_k[1], c.s_out};
+    cudaStream_t all[6] = {c.s_in, c.s_in_small, c.s_k[0], c.s_k[1], c.s_out, c.s_out_small};
     for (cudaStream_t st : all) {
       if (!st) continue;
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess && rc == DQ_OK) rc = cuda_fail(e);
     }
+  }
+  if (g_trace && !tr.empty()) {
+    const int per = bwd ? 4 : 3;
+    for (size_t i = 1; i < tr.size(); i++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tr[0], tr[i]);
+      const char* names4[] = {"in", "fwd", "bwd", "out"};
+      const char* names3[] = {"in", "fwd", "out"};
+      fprintf(stderr, "[dq host trace] chunk %zu %-3s done at %.3f ms\n", (i - 1) / per, (bwd ? names4 : names3)[(i - 1) % per], ms);
+    }
+    for (cudaEvent_t e : tr) cudaEventDestroy(e);
   }
   if (prev_dev >= 0 && device != prev_dev) cudaSetDevice(prev_dev);
   return rc;
@@ -266,15 +321,15 @@ void host_release_all() {
     for (int s = 0; s < K_MAX; s++) {
       if (c.buf[s]) cudaFree(c.buf[s]);
       c.buf[s] = nullptr; c.cap[s] = 0;
-      if (c.e_in[s]) cudaEventDestroy(c.e_in[s]);
-      if (c.e_fwd[s]) cudaEventDestroy(c.e_fwd[s]);
-      if (c.e_bwd[s]) cudaEventDestroy(c.e_bwd[s]);
-      if (c.e_free[s]) cudaEventDestroy(c.e_free[s]);
-      c.e_in[s] = c.e_fwd[s] = c.e_bwd[s] = c.e_free[s] = nullptr;
+      cudaEvent_t* ev[4] = {&c.e_in[s], &c.e_fwd[s], &c.e_bwd[s], &c.e_free[s]};
+      for (cudaEvent_t* e : ev) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
     }
-    cudaStream_t all[4] = {c.s_in, c.s_k[0], c.s_k[1], c.s_out};
-    for (cudaStream_t st : all) if (st) cudaStreamDestroy(st);
-    c.s_in = c.s_out = c.s_k[0] = c.s_k[1] = nullptr;
+    if (c.vec) cudaFree(c.vec);
+    c.vec = nullptr; c.vec_cap = 0;
+    if (c.e_small) cudaEventDestroy(c.e_small);
+    c.e_small = nullptr;
+    cudaStream_t* all[6] = {&c.s_in, &c.s_in_small, &c.s_out, &c.s_out_small, &c.s_k[0], &c.s_k[1]};
+    for (cudaStream_t* st : all) { if (*st) cudaStreamDestroy(*st); *st = nullptr; }
     c.init = false;
   }
   if (prev >= 0) cudaSetDevice(prev);

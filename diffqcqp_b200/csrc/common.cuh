@@ -2,8 +2,8 @@
 //
 // Execution model: one *tile* of T lanes (T = 8, 16 or 32, the next power of two
 // >= N, minimum 8) owns one problem; lane i of the tile owns element i of every N-vector and row i of
-// every N x N matrix.  A warp therefore carries G = 32/T problems ("a group").  Each CTA is a single
-// warp, so there is no CTA-level synchronisation anywhere: only __syncwarp and tile-local shuffles.
+// every N x N matrix.  A warp therefore carries G = 32/T problems ("a group") and never synchronises
+// with another warp: only __syncwarp, ballots and tile-local shuffles.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,86 +16,10 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 // Every lane of the tile ends with the bitwise-identical result (max/add are commutative and both
 // partners of a butterfly stage compute the same pair), so per-problem control flow stays uniform.
 template <int T>
-__device__ __forceinline__ double tile_max(double v) {
-#pragma unroll
-  for (int o = T / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
-  return v;
-}
-
-template <int T>
 __device__ __forceinline__ double tile_sum(double v) {
 #pragma unroll
   for (int o = T / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
   return v;
-}
-
-// Two max-reductions for the price of ~1.3: after the first exchange even lanes carry `a`, odd lanes
-// carry `b`; the remaining stages reduce one value per lane; a final exchange hands both back.
-template <int T>
-__device__ __forceinline__ void tile_max2(double& a, double& b, int lane) {
-  const bool odd = lane & 1;
-  double send = odd ? a : b;
-  double keep = odd ? b : a;
-  double got = __shfl_xor_sync(FULL_MASK, send, 1);
-  double v = fmax(keep, got);  // even lanes: max(a_even, a_odd); odd lanes: max(b_odd, b_even)
-#pragma unroll
-  for (int o = T / 2; o > 1; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
-  double other = __shfl_xor_sync(FULL_MASK, v, 1);
-  a = odd ? other : v;
-  b = odd ? v : other;
-}
-
-// ---------------------------------------------------------------- mbarrier + 1-D bulk copy (TMA)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-// global -> shared bulk copy, completion counted in bytes on `bar`.  dst/src 16-byte aligned,
-// bytes a multiple of 16.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-
-// Stage `count` doubles from global into shared memory.  Bulk (TMA) when both ends are 16-byte
-// aligned and the size is a multiple of 16 bytes -- returns the byte count the caller must have
-// announced with mbar_expect_tx -- otherwise an element-wise copy by the whole warp (returns 0).
-// Call with all 32 lanes.
-__device__ __forceinline__ bool bulk_eligible(const void* src, const void* dst, size_t bytes) {
-  return ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0 && bytes > 0;
-}
-
-__device__ __forceinline__ void warp_copy(double* dst, const double* __restrict__ src, int count, int lane) {
-  for (int i = lane; i < count; i += 32) dst[i] = __ldg(src + i);
 }
 
 // ---------------------------------------------------------------- in-tile SPD inverse

@@ -48,6 +48,11 @@ def qcqp_dense(B, N, seed=0, diag=False):
     return P, q, l_n, mu, grad
 
 
+def qcqp_diag(B, N, seed=0):
+    """Diagonal-P QCQP (P = diag_embed(rand + 0.1)), otherwise as qcqp_dense."""
+    return qcqp_dense(B, N, seed=seed, diag=True)
+
+
 # algorithmic bytes per solve (SURVEY.md section 8d): every input read once, every output written once.
 # warm_start is never read by the kernels (dead in the reference, F2), so its 8N bytes are NOT counted.
 def qp_bytes(N, fwd=True, bwd=True):
