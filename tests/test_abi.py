@@ -42,7 +42,9 @@ def test_identification(lib):
         assert len(lib.dq_error_string(code)) > 3
 
 
-def test_sass_is_sm100a_and_uses_bulk_copies():
+def test_sass_is_sm100a_with_256bit_global_accesses():
+    """The library holds sm_100a SASS only, and the kernels stream P / grad_P rows with the 256-bit global
+    loads/stores that exist from sm_100 on (LDG.E...256 / STG.E...256) and vote-based control (VOTE)."""
     from diffqcqp_b200 import _lib
     import shutil
     import subprocess
@@ -51,6 +53,11 @@ def test_sass_is_sm100a_and_uses_bulk_copies():
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+    archs = set(l.split(".")[-2] for l in out.splitlines() if l.strip().endswith(".cubin"))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "admm_fwd_kernel" in sass and "qp_bwd_kernel" in sass and "qcqp_bwd_kernel" in sass
+    assert ".256" in sass and "LDG" in sass and "STG" in sass and "VOTE" in sass and "DFMA" in sass
 
 
 def test_argument_validation_without_gpu(lib):

@@ -405,3 +405,68 @@ def test_cfg5_qcqp_n16_per_gpu_shard(dq, wl, oracle):
     lo, hi = 3 * B // 8, 4 * B // 8
     xs = dq.qcqp_forward(*[t[lo:hi].contiguous() for t in d], EPS, 1000)
     assert torch.equal(xs, x[lo:hi])
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def test_edge_sizes_and_layouts(dq, wl, oracle):
+    """Smallest and largest supported sizes, single problems, ragged groups, non-contiguous / float32 inputs through
+    the autograd surface (the reference's pybind11 layer converts float32 silently and accepts any strides)."""
+    import qcqp
+    for N, B in ((1, 1), (1, 33), (2, 5), (7, 3), (31, 9), (32, 1), (32, 65)):
+        P, q, g = wl.qp_dense(B, N, seed=80 + N)
+        xo, ito = oracle.qp_forward(P.numpy(), q.numpy(), None, EPS, 1000, return_iters=True)
+        x, it = dq.qp_forward(P.cuda(), q.cuda(), EPS, 1000, return_iters=True)
+        assert np.array_equal(it.cpu().numpy(), ito), (N, B)
+        check_x(x, xo, EPS)
+    for N, B in ((2, 1), (4, 7), (30, 5), (32, 3)):
+        P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=90 + N)
+        xo, ito = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, EPS, 1000, return_iters=True)
+        x, it = dq.qcqp_forward(*dev(P, q, l_n, mu), EPS, 1000, return_iters=True)
+        assert np.array_equal(it.cpu().numpy(), ito), (N, B)
+        check_x(x, xo, EPS)
+    # N above the tile limit is rejected, not mis-solved
+    with pytest.raises(Exception):
+        dq.qp_forward(torch.eye(33, dtype=torch.float64, device="cuda")[None], torch.ones(1, 33, 1, dtype=torch.float64, device="cuda"), EPS, 10)
+    # non-contiguous P (a transposed view of a symmetric batch) and float32 inputs
+    P, q, g = wl.qp_dense(50, 8, seed=99)
+    x_ref = qcqp.QPFn2.apply(P.cuda(), q.cuda(), torch.zeros_like(q).cuda(), EPS, 1000)
+    x_nc = qcqp.QPFn2.apply(P.cuda().transpose(1, 2), q.cuda(), torch.zeros_like(q).cuda(), EPS, 1000)
+    assert torch.allclose(x_nc, x_ref, rtol=0, atol=10 * EPS)
+    x32 = qcqp.QPFn2.apply(P.float().cuda(), q.float().cuda(), torch.zeros_like(q).cuda(), EPS, 1000)
+    assert x32.dtype == torch.float64
+    xo32 = oracle.qp_forward(P.float().double().numpy(), q.float().double().numpy(), None, EPS, 1000)
+    check_x(x32, xo32, EPS)
+
+
+def test_mixed_diagonal_and_dense_groups(dq, wl, oracle):
+    """The diagonal fast path is chosen per group of 32/T problems from the data: a batch that interleaves diagonal
+    and dense problems must give each problem the same answer it gets alone."""
+    Pd, qd_, _ = wl.qp_diag(64, 8, seed=71)
+    Pn, qn, _ = wl.qp_dense(64, 8, seed=72)
+    P = torch.stack([Pd, Pn], 1).reshape(128, 8, 8).contiguous()   # d, n, d, n, ... -> every group of 4 is mixed
+    q = torch.stack([qd_, qn], 1).reshape(128, 8, 1).contiguous()
+    x, it = dq.qp_forward(P.cuda(), q.cuda(), EPS, 1000, return_iters=True)
+    xo, ito = oracle.qp_forward(P.numpy(), q.numpy(), None, EPS, 1000, return_iters=True)
+    assert np.array_equal(it.cpu().numpy(), ito)
+    check_x(x, xo, EPS)
+    x_alone = dq.qp_forward(Pd.cuda(), qd_.cuda(), EPS, 1000)      # the same diagonal problems on the diagonal path
+    assert torch.allclose(x[0::2], x_alone, rtol=0, atol=10 * EPS)
+    g = torch.ones_like(q)
+    gP, gq = dq.qp_backward(P.cuda(), q.cuda(), torch.from_numpy(xo).cuda(), g.cuda())
+    gPo, gqo = oracle.qp_backward(P.numpy(), q.numpy(), xo, g.numpy())
+    assert rel_rows(gq, gqo).max() <= 1e-10 and rel_rows(gP, gPo).max() <= 1e-10
+
+
+def test_max_iter_hit_is_reported(dq, wl, oracle):
+    """Non-convergence is silent in the reference (Solver.cpp:79); here the optional iters output shows it and the
+    returned iterate is still the reference's l_2 at max_iter."""
+    P, q, _ = wl.qp_diag(256, 8, seed=73)
+    x, it = dq.qp_forward(P.cuda(), q.cuda(), 1e-14, 7, return_iters=True)
+    xo, ito = oracle.qp_forward(P.numpy(), q.numpy(), None, 1e-14, 7, return_iters=True)
+    assert np.array_equal(it.cpu().numpy(), ito) and int(it.max()) == 7
+    assert np.abs(x.cpu().numpy() - xo).max() <= 1e-12 * max(1.0, np.abs(xo).max())
+    P, q, l_n, mu, _ = wl.qcqp_dense(64, 8, seed=74)
+    x, it = dq.qcqp_forward(*dev(P, q, l_n, mu), 1e-15, 5, return_iters=True)
+    xo, ito = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, 1e-15, 5, return_iters=True)
+    assert np.array_equal(it.cpu().numpy(), ito) and int(it.max()) == 5
+    assert np.abs(x.cpu().numpy() - xo).max() <= 1e-12
