@@ -195,6 +195,13 @@ int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, 
   return it;
 }
 
+/* Test hook (not in the reference): move the initial rho by this many ulps.  pow() is libm-dependent
+ * (glibc documents < 1 ULP, not correct rounding), so the reference's own rho changes by an ulp with
+ * the C library it is linked against; the parity tests use this to measure how far the reference's
+ * result moves under that perturbation and hold the GPU to the same envelope. */
+static int g_rho_nudge = 0;
+void dq_oracle_set_rho_nudge(int ulps) { g_rho_nudge = ulps; }
+
 /* ------------------------------------------------------------ ADMM core ------------------ */
 /* Shared skeleton of Solver::solveQP (Solver.cpp:61-123) and Solver::solveQCQP (:521-582).
  * radius == NULL selects the QP (non-negative clip, :82); otherwise the per-contact disk
@@ -222,6 +229,8 @@ static int admm_solve(const double* P_in, const double* q, const double* warm_st
   }
   double L = dq_oracle_power_iteration(P, n, is_qcqp ? 100 : 10);   /* :71 / :530 */
   double rho = sqrt(mu_prox * L) * pow(L / mu_prox, .4);            /* :72 / :531 */
+  for (int k = 0; k < (g_rho_nudge < 0 ? -g_rho_nudge : g_rho_nudge); k++)   /* test hook, see dq_oracle_set_rho_nudge */
+    rho = nextafter(rho, g_rho_nudge > 0 ? INFINITY : -INFINITY);
   double tau_inc = pow(L / mu_prox, .15), tau_dec = tau_inc;        /* :73 / :532 */
   for (int i = 0; i < n; i++) P[i * n + i] += (rho + mu_prox);      /* :75 / :534 */
   spd_inverse(P, Pinv, work, n);                                    /* :76-77 / :535-536 */

@@ -59,6 +59,8 @@ double dq_oracle_power_iteration(const double* A, int n, int max_iter);
 int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, int m);
 /* Test hook: n > 0 forces exactly n refinement steps (stop rule ignored); 0 restores the reference rule. */
 void dq_oracle_set_ir_force(int n);
+/* Test hook: start the ADMM with rho moved by `ulps` ulps (what a different libm pow() does to the reference). */
+void dq_oracle_set_rho_nudge(int ulps);
 
 /* ---- batched entry points: the per-item loops of qcqp.py:22-52,141-181 in one C call ----
  * threads <= 0 means "all OpenMP threads"; threads == 1 is the reference's serial shape.

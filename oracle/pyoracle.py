@@ -80,6 +80,8 @@ def lib():
         L.dq_oracle_max_threads.restype = ctypes.c_int
         L.dq_oracle_set_ir_force.restype = None
         L.dq_oracle_set_ir_force.argtypes = [ctypes.c_int]
+        L.dq_oracle_set_rho_nudge.restype = None
+        L.dq_oracle_set_rho_nudge.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -94,6 +96,11 @@ def _p(a):
 
 def max_threads() -> int:
     return int(lib().dq_oracle_max_threads())
+
+
+def set_rho_nudge(ulps: int) -> None:
+    """Test hook: start every ADMM solve with rho moved by `ulps` ulps (0 restores the reference value)."""
+    lib().dq_oracle_set_rho_nudge(int(ulps))
 
 
 def set_ir_force(n: int) -> None:

@@ -470,3 +470,51 @@ def test_max_iter_hit_is_reported(dq, wl, oracle):
     xo, ito = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, 1e-15, 5, return_iters=True)
     assert np.array_equal(it.cpu().numpy(), ito) and int(it.max()) == 5
     assert np.abs(x.cpu().numpy() - xo).max() <= 1e-12
+
+
+def test_reference_published_workload_test_script(dq, oracle):
+    """The one workload the reference publishes a number for (README.md:65 plot, test_script.py:90-113 and :143-151):
+    N=8, P = diag(exp(U(-10,10))), q ~ U(-1,1), l_n, mu ~ U(0,1), eps = 1e-10 -- condition numbers up to e^20.
+    Relative 10*eps bar per problem, iteration counts equal
+    for all but a handful (a +-1 ulp pow() moves the stop by one iteration on such inputs)."""
+    g = torch.Generator().manual_seed(123)
+    B, N, eps = 4096, 8, 1e-10
+    p = torch.exp(20 * torch.rand(B, N, generator=g, dtype=torch.float64) - 10)
+    q = 2 * torch.rand(B, N, 1, generator=g, dtype=torch.float64) - 1
+    l_n = torch.rand(B, N // 2, 1, generator=g, dtype=torch.float64)
+    mu = torch.rand(B, N // 2, 1, generator=g, dtype=torch.float64)
+    P = torch.diag_embed(p)
+    xo, ito = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, eps, 100000, return_iters=True)
+    x, it = dq.qcqp_forward(*dev(P, q, l_n, mu), eps, 100000, return_iters=True)
+    mism = int((it.cpu().numpy() != ito).sum())
+    frac = check_x(x, xo, eps, max_abs_frac=5e-3)
+    print(f"\n[test_script QCQP] iteration mismatches {mism}/{B}, above absolute 10*eps: {frac:.2e}, iters mean {ito.mean():.1f} max {ito.max()}")
+    assert mism <= B // 500
+    gg = dq.qcqp_backward(*dev(P, q, l_n, mu), torch.from_numpy(xo).cuda(), torch.ones(B, N, 1, dtype=torch.float64, device="cuda"))
+    for t in gg:
+        assert torch.all(torch.isfinite(t))
+    # QP on the same diagonal (condition numbers up to e^20, |x| up to 1e4, ~100 iterations).  Here the reference
+    # is only reproducible to ~1e-6 relative across C libraries: moving its initial rho by ONE ulp (what a different
+    # libm pow() does) changes the iteration count of ~6 % of these problems.  The GPU is held to that envelope:
+    # no further from the oracle than the oracle's own +-1 ulp replays are (x2), and 1e-5 relative at worst.
+    # (test_script.py:143-149 raises P to the 4th power, cond e^80: on that input the reference's ADMM itself
+    # diverges -- NaN / 1e240 outputs -- so there is nothing to be in parity with; DESIGN.md section 4.)
+    Pn, qn = P.numpy(), q.numpy()
+    xo, ito = oracle.qp_forward(Pn, qn, None, eps, 100000, return_iters=True)
+    env_mism, env_far = 0, 0
+    sc = np.maximum(1.0, np.abs(xo).reshape(B, -1).max(1))
+    try:
+        for ulps in (1, -1):
+            oracle.set_rho_nudge(ulps)
+            xn, itn = oracle.qp_forward(Pn, qn, None, eps, 100000, return_iters=True)
+            env_mism = max(env_mism, int((itn != ito).sum()))
+            env_far = max(env_far, int((np.abs(xn - xo).reshape(B, -1).max(1) > 10 * eps * sc).sum()))
+    finally:
+        oracle.set_rho_nudge(0)
+    x, it = dq.qp_forward(P.cuda(), q.cuda(), eps, 100000, return_iters=True)
+    d = np.abs(x.cpu().numpy() - xo).reshape(B, -1).max(1)
+    mism, far = int((it.cpu().numpy() != ito).sum()), int((d > 10 * eps * sc).sum())
+    print(f"[test_script QP] GPU vs oracle: {mism} iteration mismatches, {far} beyond relative 10*eps, max rel {np.max(d / sc):.1e}; "
+          f"oracle vs itself at +-1 ulp of rho: {env_mism} and {env_far}; iters mean {ito.mean():.1f} max {ito.max()}")
+    assert np.all(np.isfinite(d)) and np.max(d / sc) <= 1e-5
+    assert mism <= 2 * env_mism + 4 and far <= 2 * env_far + 4
