@@ -68,6 +68,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scatter", action="store_true",
+                    help="(N>1) also time the scatter-inclusive step: rank 0 holds all N*B problems, NCCL scatter of "
+                         "(P,q[,l_n,mu],grad_l), solve, NCCL gather of x* and grad_q")
     return ap.parse_args()
 
 
@@ -214,6 +217,29 @@ def cpu_pass(eng, kind, a, threads=0):
         x = eng.qcqp_forward(a["P"], a["q"], a["l_n"], a["mu"], None, EPS, MAX_ITER, MU_PROX, threads=threads)
         eng.qcqp_backward(a["P"], a["q"], a["l_n"], a["mu"], x, a["g"], threads=threads)
     return time.perf_counter() - t0
+
+
+def as_shipped_loop(kind, inp, eng, n=2000):
+    """The reference's shipped call shape (qcqp.py:29-31, :45-47): a Python loop over the batch calling the
+    per-problem binding, one core (the GIL is held across the call).  Small sample, reported for context."""
+    import numpy as np
+
+    n = min(n, inp["P"].shape[0])
+    a = {k: np.ascontiguousarray(v[:n].numpy()) for k, v in inp.items()}
+    N = a["P"].shape[1]
+    ws = np.zeros(N)
+    t0 = time.perf_counter()
+    if kind == "qp":
+        for i in range(n):
+            x = eng.solveQP(a["P"][i], a["q"][i], ws, EPS, MU_PROX, MAX_ITER, True)
+            eng.solveDerivativesQP(a["P"][i], a["q"][i], x, a["g"][i])
+    else:
+        for i in range(n):
+            x = eng.solveQCQP(a["P"][i], a["q"][i], a["l_n"][i], a["mu"][i], ws, EPS, MU_PROX, MAX_ITER, True)
+            eng.solveDerivativesQCQP(a["P"][i], a["q"][i], a["l_n"][i], a["mu"][i], x, a["g"][i])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "solves/s", "cores": 1,
+            "sample": f"Python per-item loop over the first {n} problems (the shipped shape of qcqp.py), ctypes binding"}
 
 
 def cpu_sample(kind, inp, B, budget_s, sample=0):
@@ -437,6 +463,47 @@ def run_b200_arm(args):
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
                "api": "dq_qp_solve_host" if kind == "qp" else "dq_qcqp_solve_host"}
 
+    # ---- scatter-inclusive step (N>1, --scatter): rank 0 owns all world*B problems; NCCL point-to-point scatter of the
+    # inputs, the sharded solve, gather of x* and grad_q (grad_P stays sharded: it is 8N^2 bytes per problem)
+    scatter_line = None
+    if distributed and args.scatter:
+        from diffqcqp_b200 import shard
+
+        keys = ["P", "q", "g"] + (["l_n", "mu"] if kind == "qcqp" else [])
+        full = None
+        if rank == 0:
+            full = [torch.cat([sets[0][k]] * world, 0) for k in keys]
+        trailing = [tuple(sets[0][k].shape[1:]) for k in keys]
+        d = sets[0]
+
+        def scatter_step():
+            parts = shard.scatter_batch(full, B * world, src=0, device=dev, trailing=trailing)
+            loc = dict(zip(keys, parts))
+            loc.update(x=d["x"], gP=d["gP"], gq=d["gq"])
+            if kind == "qcqp":
+                loc.update(gl=d["gl"], gm=d["gm"])
+            fwd(loc); bwd(loc)
+            shard.gather_batch(loc["x"], B * world, dst=0)
+            shard.gather_batch(loc["gq"], B * world, dst=0)
+
+        for _ in range(3):
+            scatter_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nsc = 20
+        e0.record(stream)
+        for _ in range(nsc):
+            scatter_step()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / nsc], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sc_ms = float(t.item())
+        in_bytes = sum(int(f.numel()) * 8 for f in full) * (world - 1) // world if rank == 0 else 0
+        scatter_line = {"ms_per_step": sc_ms, "value": B * world / (sc_ms * 1e-3), "unit": "solves/s",
+                        "root_egress_bytes_per_step": in_bytes,
+                        "note": "rank 0 scatters (P,q,grad_l[,l_n,mu]) over NCCL send/recv, every rank solves its shard, x* and grad_q are gathered on rank 0"}
+
     if distributed:
         t = torch.tensor([total_ms, fwd_avg, bwd_avg], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -479,6 +546,9 @@ def run_b200_arm(args):
             dt = sum(cpu_pass(eng, kind, a) for _ in range(reps))
             line["cpu_baseline"] = {"value": n * reps / dt, "unit": "solves/s", "cores": host_threads(), "kind": ckind,
                                     "sample": f"{reps} x (fwd+bwd over the first {n} of {B} problems), OpenMP over problems, {dt:.1f} s"}
+            line["cpu_baseline"]["as_shipped"] = as_shipped_loop(kind, host0, eng)
+        if scatter_line is not None:
+            line["scatter_inclusive"] = scatter_line
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
