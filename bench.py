@@ -302,6 +302,15 @@ def run_b200_arm(args):
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not os.path.exists(_lib.LIB_PATH):  # a checkout without the built artefact: rank 0 compiles it, the others wait
+        if rank == 0:
+            from diffqcqp_b200 import build as dq_build
+            dq_build.build()
+        else:
+            t_wait = time.time()
+            while not os.path.exists(_lib.LIB_PATH) and time.time() - t_wait < 300:
+                time.sleep(1.0)
+            time.sleep(2.0)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
