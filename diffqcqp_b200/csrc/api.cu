@@ -61,7 +61,8 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
 
 int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n, const double* mu,
                   const double* x, const double* grad_x, double* grad_P, double* grad_q, double* grad_l_n,
-                  double* grad_mu, long long B, int N, cudaStream_t stream) {
+                  double* grad_mu, long long B, int N, cudaStream_t stream, double* gamma = nullptr,
+                  double* dgamma = nullptr) {
   int rc = check_common(P, q, x, B, N);
   if (rc != DQ_OK) return rc;
   if (B > 0 && !grad_x) return DQ_ERR_BAD_ARG;
@@ -72,12 +73,13 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
     if (!aligned8(l_n) || !aligned8(mu) || !aligned8(grad_l_n) || !aligned8(grad_mu)) return DQ_ERR_ALIGN;
   }
   if (B == 0) return DQ_OK;
-  if (!grad_P && !grad_q && !(qcqp && (grad_l_n || grad_mu))) return DQ_OK;  // nothing requested
+  if (!grad_P && !grad_q && !(qcqp && (grad_l_n || grad_mu || gamma || dgamma))) return DQ_OK;  // nothing requested
   const int T = dq::tile_width(N);
   const int G = 32 / T;
   dq::BwdParams p;
   p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.grad_x = grad_x;
   p.grad_P = grad_P; p.grad_q = grad_q; p.grad_l_n = grad_l_n; p.grad_mu = grad_mu;
+  p.gamma = gamma; p.dgamma = dgamma;
   p.B = B; p.N = N;
   p.n_groups = (B + G - 1) / G;
   cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, stream) : dq::launch_qp_bwd(p, T, stream);
@@ -384,6 +386,14 @@ int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const 
                      int64_t B, int32_t N, void* stream) {
   return backward_impl(true, P, q, l_n, mu, x, grad_x, grad_P, grad_q, grad_l_n, grad_mu, B, N,
                        (cudaStream_t)stream);
+}
+
+int dq_qcqp_backward_ex(const double* P, const double* q, const double* l_n, const double* mu, const double* x,
+                        const double* grad_x, double* grad_P, double* grad_q, double* grad_l_n, double* grad_mu,
+                        double* gamma, double* dgamma, int64_t B, int32_t N, void* stream) {
+  if (!aligned8(gamma) || !aligned8(dgamma)) return DQ_ERR_ALIGN;
+  return backward_impl(true, P, q, l_n, mu, x, grad_x, grad_P, grad_q, grad_l_n, grad_mu, B, N, (cudaStream_t)stream,
+                       gamma, dgamma);
 }
 
 int dq_qp_solve_host(const double* P, const double* q, double* x, const double* grad_x, double* grad_P,

@@ -33,6 +33,8 @@ struct BwdParams {
   double* grad_q;    // nullable
   double* grad_l_n;  // nullable, QCQP only
   double* grad_mu;   // nullable, QCQP only
+  double* gamma;     // nullable, QCQP only: the duals of dualFromPrimalQCQP (B, N/2)
+  double* dgamma;    // nullable, QCQP only: blgamma[:nc] of solveDerivativesQCQP (B, N/2)
   long long B;
   int N;
   long long n_groups;  // ceil(B / (32/T)): one warp per group

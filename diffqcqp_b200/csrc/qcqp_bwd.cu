@@ -276,6 +276,8 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       if (p.grad_q) p.grad_q[prob * N + ti] = -dl;                      // qcqp.py:176
       if (even && p.grad_l_n) p.grad_l_n[prob * nc + c] = E2 * dgamma;  // qcqp.py:178
       if (even && p.grad_mu) p.grad_mu[prob * nc + c] = E1 * dgamma;    // qcqp.py:180
+      if (even && p.gamma) p.gamma[prob * nc + c] = gamma;              // pybindings.cpp:67 (legacy per-item API)
+      if (even && p.dgamma) p.dgamma[prob * nc + c] = dgamma;           // blgamma[:nc]  pybindings.cpp:69
     }
     if (p.grad_P) {  // qcqp.py:174  grad_P = -dl l^T : lane ti writes row ti
       xb[lane] = li;

@@ -85,6 +85,17 @@ int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const 
                      double* grad_l_n, double* grad_mu, int64_t B, int32_t N, void* stream);
 
 /*
+ * dq_qcqp_backward plus the two intermediate vectors the reference's per-problem binding returns
+ * (pybindings.cpp:62-71): gamma (B,N/2) = dualFromPrimalQCQP and dgamma (B,N/2) = blgamma[:nc] of
+ * solveDerivativesQCQP; blgamma[nc:] is -grad_q and E1 = diag(2 gamma l_n^2 mu), E2 = diag(2 gamma l_n mu^2)
+ * (Solver.cpp:683-691) follow from gamma.  Any output may be NULL.  Used by the legacy per-item module.
+ */
+int dq_qcqp_backward_ex(const double* P, const double* q, const double* l_n, const double* mu,
+                        const double* x, const double* grad_x, double* grad_P, double* grad_q,
+                        double* grad_l_n, double* grad_mu, double* gamma, double* dgamma, int64_t B,
+                        int32_t N, void* stream);
+
+/*
  * Host-buffer path (what a caller holding CPU arrays, like the reference's users, calls): copies
  * the inputs host->device in chunks on three streams so that the copy of one chunk overlaps the
  * solve of another and the read-back of a third, runs forward (and, when grad_x != NULL,

@@ -518,3 +518,77 @@ def test_reference_published_workload_test_script(dq, oracle):
           f"oracle vs itself at +-1 ulp of rho: {env_mism} and {env_far}; iters mean {ito.mean():.1f} max {ito.max()}")
     assert np.all(np.isfinite(d)) and np.max(d / sc) <= 1e-5
     assert mism <= 2 * env_mism + 4 and far <= 2 * env_far + 4
+
+
+# ------------------------------------------------------------------------------------ legacy per-item / unbatched surfaces
+def test_legacy_per_item_module_matches_oracle(cuda_lib, oracle):
+    """`from diffqcqp import solveQP, ...` (pybindings.cpp:76-82): one problem, numpy in / numpy out, binding defaults."""
+    import diffqcqp as legacy
+    r = np.random.default_rng(5)
+    for n in (2, 8, 13):
+        S = 2 * r.random((n, n)) - 1
+        P, q, g = S @ S.T / n + 0.1 * np.eye(n), 2 * r.random(n) - 1, 2 * r.random(n) - 1
+        x = legacy.solveQP(P, q, np.zeros(n))                       # epsilon=1e-10, mu_prox=1e-7, max_iter=1000, adaptative
+        xo = oracle.solveQP(P, q, np.zeros(n))
+        assert x.shape == (n,) and np.abs(x - xo).max() <= 1e-9 * max(1, np.abs(xo).max())
+        bl = legacy.solveDerivativesQP(P, q, xo, g)
+        blo = oracle.solveDerivativesQP(P, q, xo, g)
+        assert bl.shape == (n,) and np.abs(bl - blo).max() <= 1e-10 * max(1, np.abs(blo).max())
+    for n in (2, 8, 16):
+        nc = n // 2
+        S = 2 * r.random((n, n)) - 1
+        P, q, g = S @ S.T / n + 0.1 * np.eye(n), 2 * r.random(n) - 1, 2 * r.random(n) - 1
+        l_n, mu = 2 * r.random(nc) + 50, r.random(nc) + 1          # interior contacts: a well-conditioned backward
+        x = legacy.solveQCQP(P, q, l_n, mu, np.zeros(n), 1e-7)
+        xo = oracle.solveQCQP(P, q, l_n, mu, np.zeros(n), 1e-7)
+        assert np.abs(x - xo).max() <= 1e-6
+        E1, E2, blg = legacy.solveDerivativesQCQP(P, q, l_n, mu, xo, g)
+        E1o, E2o, blgo = oracle.solveDerivativesQCQP(P, q, l_n, mu, xo, g)
+        assert E1.shape == (nc, nc) and blg.shape == (nc + n,)
+        assert np.allclose(E1, E1o, rtol=1e-12, atol=0) and np.allclose(E2, E2o, rtol=1e-12, atol=0)
+        assert np.abs(blg - blgo).max() <= 1e-9 * max(1, np.abs(blgo).max())
+    # active contacts: gamma != 0, E1/E2 non-trivial; dgamma/dl follow one of the oracle's refinement iterates
+    n, nc = 8, 4
+    S = 2 * r.random((n, n)) - 1
+    P, q, g = S @ S.T / n + 0.1 * np.eye(n), 3 * (2 * r.random(n) - 1), 2 * r.random(n) - 1
+    l_n, mu = 0.1 * r.random(nc) + 0.05, r.random(nc) + 0.5
+    xo = oracle.solveQCQP(P, q, l_n, mu, np.zeros(n), 1e-7)
+    E1, E2, blg = legacy.solveDerivativesQCQP(P, q, l_n, mu, xo, g)
+    E1o, E2o, _ = oracle.solveDerivativesQCQP(P, q, l_n, mu, xo, g)
+    assert np.abs(np.diag(E1o)).max() > 0 and np.allclose(E1, E1o, rtol=1e-10, atol=1e-300) and np.allclose(E2, E2o, rtol=1e-10, atol=1e-300)
+    best = np.inf
+    try:
+        for k in (1, 2, 3, 4, 5):
+            oracle.set_ir_force(k)
+            best = min(best, np.abs(blg - oracle.solveDerivativesQCQP(P, q, l_n, mu, xo, g)[2]).max())
+    finally:
+        oracle.set_ir_force(0)
+    assert best <= 1e-6 * max(1, np.abs(blg).max())
+    with pytest.raises(NotImplementedError):
+        legacy.solveBoxQP(P, q, -np.ones(n), np.ones(n), np.zeros(n))
+
+
+def test_unbatched_layers(cuda_lib, oracle):
+    """qcqp_no_batch.py:23-108: P (N,N), q (N,1) -> l (N,), gradients shaped like the inputs."""
+    import qcqp_no_batch as nb
+    r = np.random.default_rng(6)
+    n = 8
+    S = 2 * r.random((n, n)) - 1
+    P = torch.tensor(S @ S.T / n + 0.1 * np.eye(n), requires_grad=True)
+    q = torch.tensor(2 * r.random((n, 1)) - 1, requires_grad=True)
+    l = nb.QPFn2.apply(P, q, torch.zeros(n, 1), 1e-7, 1000)
+    assert l.shape == (n,)
+    xo = oracle.solveQP(P.detach().numpy(), q.detach().numpy(), np.zeros(n), 1e-7)
+    assert np.abs(l.detach().numpy() - xo).max() <= 1e-6
+    l.sum().backward()
+    assert P.grad.shape == (n, n) and q.grad.shape == (n, 1)
+    blo = oracle.solveDerivativesQP(P.detach().numpy(), q.detach().numpy(), l.detach().numpy(), np.ones(n))
+    assert np.abs(q.grad.numpy()[:, 0] + blo).max() <= 1e-9
+    l_n = torch.tensor(r.random((n // 2, 1)) + 0.5, requires_grad=True)
+    mu = torch.tensor(r.random((n // 2, 1)), requires_grad=True)
+    P2, q2 = P.detach().clone().requires_grad_(True), q.detach().clone().requires_grad_(True)
+    l = nb.QCQPFn2.apply(P2, q2, l_n, mu, torch.zeros(n, 1), 1e-7, 1000)
+    xo = oracle.solveQCQP(P2.detach().numpy(), q2.detach().numpy(), l_n.detach().numpy(), mu.detach().numpy(), np.zeros(n), 1e-7)
+    assert l.shape == (n,) and np.abs(l.detach().numpy() - xo).max() <= 1e-6
+    l.sum().backward()
+    assert P2.grad.shape == (n, n) and q2.grad.shape == (n, 1) and l_n.grad.shape == (n // 2, 1) and mu.grad.shape == (n // 2, 1)
