@@ -11,7 +11,7 @@ are independent, so there is no collective on the data path (weak scaling).
 
 Timed region (``value``): inputs resident in HBM, K steps over R rotating input sets whose total
 footprint exceeds the 126 MB L2 (so no step finds its inputs cached from the previous use), issued
-round-robin on ``--streams`` CUDA streams (default 2: fwd -> bwd of one batch stay ordered, independent
+round-robin on ``--streams`` CUDA streams (default 4: fwd -> bwd of one batch stay ordered, independent
 batches overlap), bracketed by barrier + synchronize, CUDA events on the launching stream (the side
 streams fork from and join into it), max over ranks.  ``config.single_stream_ms_per_step`` is the same
 loop on one stream.
@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the timed steps are issued on round-robin (independent batches overlap)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="qp_diag_n8", choices=sorted(WORKLOADS))
