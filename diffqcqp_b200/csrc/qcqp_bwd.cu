@@ -110,6 +110,16 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       }
     }
 
+    // is every problem of this group diagonal?  (decided from the data, warp-uniform)
+    double pd = 0.0;
+    bool nzoff = false;
+#pragma unroll
+    for (int j = 0; j < T; j++) {
+      if (j == ti) pd = drow[j];
+      else nzoff |= (drow[j] != 0.0);
+    }
+    const bool diagP = !__any_sync(FULL_MASK, nzoff);
+
     // ---- dualFromPrimalQCQP (Solver.cpp:584-617)
     vb[ti] = li;
     __syncwarp();
@@ -146,6 +156,75 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     const double rsa_c = 1.0 / sa_c;
     const double rhs1 = act ? (bt0 * ge0 + bt1 * ge1) : 0.0;      // (G dd)_j = B_tild(j,:) grad_l
 
+    double x1 = 0.0, x2 = 0.0;  // the refinement iterate: x1 = dgamma of this contact (lane pair), x2 = dl of this lane
+    if (diagP) {
+      // ---- diagonal P: D = P + blkdiag(2 gamma_c I2) is diagonal, so G G^T + mu I is block diagonal with one
+      // 3 x 3 block [dgamma_c; dl_2c; dl_2c+1] per active contact (2 x 2 diagonal for an inactive one).  Same block
+      // elimination as the general path below, with every length-T sum reduced to its one or two non-zero terms;
+      // the partner lane of the pair (xor 1) supplies the other row.  Only the residual norm couples contacts.
+      const double d = 2 * gamma + pd;                            // D(ti,ti)   :656
+      const double rhs2 = d * gi;                                 // (D grad_l)_i
+      const double cvi = act ? fma(d, even ? bt0 : bt1, (2 * li) * slack) : 0.0;  // A21(ti, c)
+      const double wi = cvi * (act ? rsa_c : 0.0);                // L21(ti, c)
+      const double wo = __shfl_xor_sync(FULL_MASK, wi, 1);
+      const double a_ii = fma(d, d, act ? (2 * li) * (2 * li) : 0.0) + MU_IR;     // A22(ti,ti)
+      const double a_io = act ? (2 * li) * (2 * lo) : 0.0;                         // A22(ti,partner)
+      const double s_ii = valid ? a_ii - wi * wi : 1.0;           // Schur complement of the pair (padded lanes: identity)
+      const double s_io = valid ? a_io - wi * wo : 0.0;
+      const double s_oo = __shfl_xor_sync(FULL_MASK, s_ii, 1);
+      const double S00 = even ? s_ii : s_oo, S11 = even ? s_oo : s_ii, S01 = s_io;
+      // 2 x 2 Cholesky and inverse, pivots applied as rsqrt multiplications like tile_spd_inverse
+      const double rp0 = rsqrt(S00);
+      const double L10 = S01 * rp0;
+      const double rp1 = rsqrt(S11 - L10 * L10);
+      double inv_i0, inv_i1;  // row ti of the inverse: (inv(ti,0), inv(ti,1)) in pair coordinates
+      {
+        // column 0: y = (rp0, -L10 rp0 rp1), x1 = y1 rp1, x0 = (y0 - L10 x1) rp0 ; column 1: y = (0, rp1)
+        const double y0 = rp0, y1 = (0.0 - L10 * y0) * rp1;
+        const double c0x1 = y1 * rp1, c0x0 = (y0 - L10 * c0x1) * rp0;
+        const double c1x1 = rp1 * rp1, c1x0 = (0.0 - L10 * c1x1) * rp0;
+        inv_i0 = even ? c0x0 : c0x1;  // inverse is symmetric: row ti == column ti
+        inv_i1 = even ? c1x0 : c1x1;
+      }
+      auto apply_inv = [&](double t1, double t2, double& b1, double& b2) {
+        const double y1 = t1 * rsa_c;                              // L11 y1 = t1
+        const double v = valid ? (t2 - wi * (act ? y1 : 0.0)) : 0.0;  // t2 - L21 y1
+        const double vo = __shfl_xor_sync(FULL_MASK, v, 1);
+        const double v0 = even ? v : vo, v1 = even ? vo : v;
+        b2 = fma(inv_i0, v0, inv_i1 * v1);                         // Schur^-1 (...)
+        const double wb = wi * b2;
+        const double acc2 = wb + __shfl_xor_sync(FULL_MASK, wb, 1);  // (L21^T b2)_c
+        b1 = act ? (y1 - acc2) * rsa_c : 0.0;                      // L11^T b1 = y1 - L21^T b2
+      };
+      auto apply_AA = [&](double xa, double xb_, double& top, double& bot) {
+        const double xo = __shfl_xor_sync(FULL_MASK, xb_, 1);
+        bot = fma(cvi, act ? xa : 0.0, fma(a_ii, xb_, a_io * xo));  // A21 x1 + A22 x2
+        const double wx = wi * xb_;
+        const double acc3 = wx + __shfl_xor_sync(FULL_MASK, wx, 1);  // L21^T x2
+        top = act ? (a_c * xa + sa_c * acc3) : 0.0;                // A12 x2 = L11 L21^T x2
+      };
+      double w1, w2;
+      apply_inv(rhs1, rhs2, w1, w2);  // AA_tild_inv * Ab  :27
+      double res_pred = 1.7976931348623157e308;
+      int ni = 0;
+      bool irdone = !vprob;
+      for (int it = 0; it < 10; ++it) {
+        if (!__any_sync(FULL_MASK, !irdone)) break;
+        double t1, t2;
+        apply_inv(x1, x2, t1, t2);
+        const double xn1 = MU_IR * t1 + w1, xn2 = MU_IR * t2 + w2;  // :29
+        double top, bot;
+        apply_AA(xn1, xn2, top, bot);
+        const double d1 = (act && even) ? (top - rhs1) : 0.0;       // contact rows counted once per pair
+        const double d2 = valid ? (bot - rhs2) : 0.0;
+        const double res = sqrt(tile_sum<T>(d1 * d1 + d2 * d2));    // :30-31
+        if (!irdone) {
+          x1 = xn1; x2 = xn2;
+          if (res_pred - res < EPS_IR) { ni++; } else { res_pred = res; ni = 0; }
+          if (res < EPS_IR || ni == 2) irdone = true;
+        }
+      }
+    } else {
 #pragma unroll
     for (int j = 0; j < T; j++)
       if (j == ti) drow[j] = 2 * gamma + drow[j];  // D_tild = D_tild + P  :656
@@ -250,7 +329,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
 
     double w1, w2;
     apply_inv(rhs1, rhs2, w1, w2);  // AA_tild_inv * Ab  :27
-    double x1 = 0.0, x2 = 0.0, res_pred = 1.7976931348623157e308;
+    double res_pred = 1.7976931348623157e308;
     int ni = 0;
     bool irdone = !vprob;
     for (int it = 0; it < 10; ++it) {
@@ -268,6 +347,8 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
         if (res_pred - res < EPS_IR) { ni++; } else { res_pred = res; ni = 0; }
         if (res < EPS_IR || ni == 2) irdone = true;
       }
+    }
+
     }
 
     const double dgamma = act ? x1 : 0.0;  // blgamma(not_null[i]) = b(i), others 0   :672-675
