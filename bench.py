@@ -550,7 +550,7 @@ def run_b200_arm(args):
                                  "kernel_ms are isolated launches on one stream"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (the reference arm covers N>1)
             eng, ckind, a, n, reps = cpu_sample(kind, host0, B, 10.0, args.cpu_sample)
             dt = sum(cpu_pass(eng, kind, a) for _ in range(reps))
             line["cpu_baseline"] = {"value": n * reps / dt, "unit": "solves/s", "cores": host_threads(), "kind": ckind,
