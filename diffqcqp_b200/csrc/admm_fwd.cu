@@ -121,8 +121,11 @@ __device__ __forceinline__ double tile_pow2_rescale(double w) {
   return __hiloint2double((int)(se << 20), 0);
 }
 
+enum : int { PROX_NONNEG = 0, PROX_DISK = 1, PROX_BOX = 2, PROX_SIGNED_BOX = 3 };  // z-update of solveQP / solveQCQP / solveBoxQP / solveSignedBoxQP
+
 struct FwdTile {  // what one lane knows about its problem when the ADMM loop starts
   double qi, pdiag, radius, rho, tau;
+  double lo, hi, vs;  // box bounds and sign(v) of this element (Box / SignedBox QP)
   const double* Prow;
   bool valid, vprob, vec32;
 };
@@ -143,9 +146,10 @@ struct FwdTile {  // what one lane knows about its problem when the ADMM loop st
 // chain of iteration k.  When rho does change (a few times per solve) the speculative iteration is
 // recomputed with the new rho; when the tile stops it is dropped.  Results are identical to the
 // unpipelined order.  A finished tile keeps executing with its answer frozen until the warp is done.
-template <int T, bool QCQP, bool DENSE>
+template <int T, int PROX, bool DENSE>
 __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t, double* Lb, double* db,
                                             double* vbuf, int& cur, int lane, int ti, int tile_base, int* it_out) {
+  constexpr bool QCQP = (PROX == PROX_DISK);
   const int N = p.N;
   const double mu = p.mu_prox, eps = p.eps;
   const bool odd = lane & 1;
@@ -181,8 +185,16 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
     const double relax = __dadd_rn(__dmul_rn(1.5, l), __dmul_rn(-0.5, s.l2));    // alpha l + (1-alpha) l_2_pred
     const double z = __dadd_rn(relax, div_by(s.u, rho, irho));                   // :82   ... + u/rho
     double l2n;
-    if (!QCQP) {
+    if (PROX == PROX_NONNEG) {
       l2n = z < 0 ? 0.0 : z;  // cwiseMax(0)
+    } else if (PROX == PROX_BOX || PROX == PROX_SIGNED_BOX) {  // solveBoxQP :219-220 / solveSignedBoxQP :396-398
+      l2n = z < t.lo ? t.lo : z;           // cwiseMax(l_min)
+      l2n = t.hi < l2n ? t.hi : l2n;       // cwiseMin(l_max)
+      if (PROX == PROX_SIGNED_BOX) {       // v.asDiagonal() * ((v.asDiagonal() * l_2).cwiseMin(0)), v = sign(v)
+        double w = __dmul_rn(t.vs, l2n);
+        w = 0 < w ? 0.0 : w;
+        l2n = __dmul_rn(t.vs, w);
+      }
     } else {                  // prox_circle :505-519
       const double zo = __shfl_xor_sync(FULL_MASK, z, 1);
       const double a0 = odd ? zo : z, a1 = odd ? z : zo;
@@ -301,9 +313,10 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
   return ans;
 }
 
-template <int T, bool QCQP>
+template <int T, int PROX>
 __global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : 16) / FWD_WARPS)
     admm_fwd_kernel(const FwdParams p) {
+  constexpr bool QCQP = (PROX == PROX_DISK);
   constexpr int G = 32 / T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.N;
@@ -336,6 +349,17 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : 16) / FWD_WARPS
     const int nc = N >> 1;
     if (t.valid)  // mul_n = l_n o mu   pybindings.cpp:57
       t.radius = __dmul_rn(__ldg(p.l_n + prob * nc + (ti >> 1)), __ldg(p.mu + prob * nc + (ti >> 1)));
+  }
+  t.lo = t.hi = t.vs = 0.0;
+  if (PROX == PROX_BOX || PROX == PROX_SIGNED_BOX) {
+    if (t.valid) {
+      t.lo = __ldg(p.lo + prob * N + ti);
+      t.hi = __ldg(p.hi + prob * N + ti);
+      if (PROX == PROX_SIGNED_BOX) {
+        const double v = __ldg(p.vsign + prob * N + ti);
+        t.vs = v > 0 ? 1.0 : (v < 0 ? -1.0 : 0.0);  // v.cwiseSign()  Solver.cpp:391
+      }
+    }
   }
   t.pdiag = 1.0;
   bool nz = false;
@@ -388,34 +412,37 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : 16) / FWD_WARPS
   }
 
   int it;
-  const double x = dense ? admm_loop<T, QCQP, true>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it)
-                         : admm_loop<T, QCQP, false>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it);
+  const double x = dense ? admm_loop<T, PROX, true>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it)
+                         : admm_loop<T, PROX, false>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it);
   if (t.valid) p.x[prob * N + ti] = x;
   if (t.vprob && ti == 0 && p.iters) p.iters[prob] = it;
 }
 
-template <int T, bool QCQP>
+template <int T, int PROX>
 static cudaError_t launch_fwd_t(const FwdParams& p, cudaStream_t stream) {
   static_assert(FwdSmem<T>::bytes <= 48 * 1024, "forward scratch must fit the default dynamic shared memory limit");
   const long long grid = (p.n_groups + FWD_WARPS - 1) / FWD_WARPS;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  admm_fwd_kernel<T, QCQP><<<(unsigned)grid, FWD_WARPS * 32, FwdSmem<T>::bytes, stream>>>(p);
+  admm_fwd_kernel<T, PROX><<<(unsigned)grid, FWD_WARPS * 32, FwdSmem<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, cudaStream_t stream) {
-  if (qcqp) {
-    switch (T) {
-      case 8: return launch_fwd_t<8, true>(p, stream);
-      case 16: return launch_fwd_t<16, true>(p, stream);
-      default: return launch_fwd_t<32, true>(p, stream);
-    }
-  } else {
-    switch (T) {
-      case 8: return launch_fwd_t<8, false>(p, stream);
-      case 16: return launch_fwd_t<16, false>(p, stream);
-      default: return launch_fwd_t<32, false>(p, stream);
-    }
+template <int PROX>
+static cudaError_t launch_fwd_p(const FwdParams& p, int T, cudaStream_t stream) {
+  switch (T) {
+    case 8: return launch_fwd_t<8, PROX>(p, stream);
+    case 16: return launch_fwd_t<16, PROX>(p, stream);
+    default: return launch_fwd_t<32, PROX>(p, stream);
+  }
+}
+
+// prox: 0 = x >= 0 (QP), 1 = per-contact disks (QCQP), 2 = box, 3 = box + sign constraint
+cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t stream) {
+  switch (prox) {
+    case PROX_NONNEG: return launch_fwd_p<PROX_NONNEG>(p, T, stream);
+    case PROX_DISK: return launch_fwd_p<PROX_DISK>(p, T, stream);
+    case PROX_BOX: return launch_fwd_p<PROX_BOX>(p, T, stream);
+    default: return launch_fwd_p<PROX_SIGNED_BOX>(p, T, stream);
   }
 }
 

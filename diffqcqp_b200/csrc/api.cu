@@ -38,7 +38,8 @@ int check_common(const void* P, const void* q, const void* x, long long B, int N
 
 int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n, const double* mu, double* x,
                  int32_t* iters, long long B, int N, double eps, double mu_prox, int max_iter, int adaptive,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const double* l_min = nullptr, const double* l_max = nullptr,
+                 const double* v = nullptr) {
   int rc = check_common(P, q, x, B, N);
   if (rc != DQ_OK) return rc;
   if (qcqp) {
@@ -51,9 +52,11 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
   const int G = 32 / T;
   dq::FwdParams p;
   p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.iters = iters;
+  p.lo = l_min; p.hi = l_max; p.vsign = v;
   p.B = B; p.N = N; p.eps = eps; p.mu_prox = mu_prox; p.max_iter = max_iter; p.adaptive = adaptive ? 1 : 0;
   p.n_groups = (B + G - 1) / G;
-  cudaError_t e = dq::launch_admm_fwd(p, qcqp, T, stream);
+  const int prox = qcqp ? 1 : (l_min ? (v ? 3 : 2) : 0);
+  cudaError_t e = dq::launch_admm_fwd(p, prox, T, stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DQ_OK;
@@ -386,6 +389,16 @@ int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const 
                      int64_t B, int32_t N, void* stream) {
   return backward_impl(true, P, q, l_n, mu, x, grad_x, grad_P, grad_q, grad_l_n, grad_mu, B, N,
                        (cudaStream_t)stream);
+}
+
+int dq_boxqp_forward(const double* P, const double* q, const double* l_min, const double* l_max, const double* v,
+                     const double* warm_start, double* x, int32_t* iters, int64_t B, int32_t N, double eps,
+                     double mu_prox, int32_t max_iter, int32_t adaptative_rho, void* stream) {
+  (void)warm_start;  // dead in the reference: Solver.cpp:207 -> :217, :383 -> :394
+  if (B > 0 && (!l_min || !l_max)) return DQ_ERR_BAD_ARG;
+  if (!aligned8(l_min) || !aligned8(l_max) || !aligned8(v)) return DQ_ERR_ALIGN;
+  return forward_impl(false, P, q, nullptr, nullptr, x, iters, B, N, eps, mu_prox, max_iter, adaptative_rho,
+                      (cudaStream_t)stream, l_min, l_max, v);
 }
 
 int dq_qcqp_backward_ex(const double* P, const double* q, const double* l_n, const double* mu, const double* x,

@@ -11,6 +11,9 @@ struct FwdParams {
   const double* q;
   const double* l_n;  // QCQP only
   const double* mu;   // QCQP only
+  const double* lo;     // Box / SignedBox QP only: l_min
+  const double* hi;     // Box / SignedBox QP only: l_max
+  const double* vsign;  // SignedBox QP only: v
   double* x;
   int32_t* iters;  // nullable
   long long B;
@@ -44,7 +47,8 @@ struct BwdParams {
 inline int tile_width(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
 
 size_t fwd_smem_bytes(int T);
-cudaError_t launch_admm_fwd(const FwdParams& p, bool qcqp, int T, cudaStream_t stream);
+// prox: 0 = x >= 0 (solveQP), 1 = per-contact disks (solveQCQP), 2 = box (solveBoxQP), 3 = box + sign (solveSignedBoxQP)
+cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t stream);
 cudaError_t launch_qp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 

@@ -26,7 +26,8 @@ from torch.autograd import Function
 
 from . import _lib
 
-__all__ = ["QPFn2", "QCQPFn2", "qp_forward", "qp_backward", "qcqp_forward", "qcqp_backward"]
+__all__ = ["QPFn2", "QCQPFn2", "BoxQPFn2", "SignedBoxQPFn2", "qp_forward", "qp_backward", "qcqp_forward",
+           "qcqp_backward", "boxqp_forward"]
 
 
 def _ptr(t):
@@ -138,6 +139,20 @@ def qcqp_backward(P, q, l_n, mu, x, grad_x, need=(True, True, True, True)):
     return gP, gq, gl, gm
 
 
+def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, v=None, return_iters=False):
+    """Batched solveBoxQP (v is None) / solveSignedBoxQP on CUDA tensors: l_min, l_max[, v] are (B,N,1)."""
+    dev = P.device
+    B, N = P.size(0), P.size(1)
+    x = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
+    iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
+    L = _lib.load()
+    with torch.cuda.device(dev):
+        rc = L.dq_boxqp_forward(_ptr(P), _ptr(q), _ptr(l_min), _ptr(l_max), _ptr(v), None, _ptr(x), _ptr(iters), B, N,
+                                float(eps), float(mu_prox), int(max_iter), int(bool(adaptative_rho)), _stream_ptr(dev))
+    _lib.check(rc, "dq_boxqp_forward")
+    return (x, iters) if return_iters else x
+
+
 def _back_to(t, device):
     if t is None or t.device == device:
         return t
@@ -187,3 +202,49 @@ class QCQPFn2(Function):
         gP, gq, gl, gm = qcqp_backward(Pd, qd, ld, md, x, g, tuple(ctx.needs_input_grad[:4]))
         o = ctx.out_device
         return _back_to(gP, o), _back_to(gq, o), _back_to(gl, o), _back_to(gm, o), None, None, None, None
+
+
+def _check_box(P, q, *bounds):
+    B, N = _check_shapes(P, q)
+    for nm, t in bounds:
+        if tuple(t.shape) != (B, N, 1):
+            raise ValueError(f"{nm} must have shape (B,N,1)=({B},{N},1), got {tuple(t.shape)}")
+
+
+class BoxQPFn2(Function):
+    """min 1/2 l'Pl + q'l  s.t. l_min <= l <= l_max, batched.  Forward mirrors qcqp.py:56-66 (solveBoxQP).
+
+    SURVEY.md 8(f) row 1.  The reference's Python backward for this class cannot run as shipped (it unpacks six names
+    from four values, swaps l_min/l_max when reading the saved tensors and calls a method torch does not have,
+    qcqp.py:72-93), so there is no reference behaviour to reproduce yet: backward raises until the C++
+    solveDerivativesBoxQP path (Solver.cpp:303-371) has its own kernel."""
+
+    @staticmethod
+    def forward(ctx, P, q, l_min, l_max, warm_start, eps, max_iter, mu_prox=1e-7):
+        _check_box(P, q, ("l_min", l_min), ("l_max", l_max))
+        dev = _compute_device(P, q, l_min, l_max)
+        t = [_as_dev(a, dev, n) for a, n in ((P, "P"), (q, "q"), (l_min, "l_min"), (l_max, "l_max"))]
+        x = boxqp_forward(*t, eps, max_iter, mu_prox, True)
+        return _back_to(x, q.device)
+
+    @staticmethod
+    def backward(ctx, grad_l):
+        raise NotImplementedError("BoxQPFn2.backward: the reference's own backward does not run (qcqp.py:72-93); "
+                                  "not part of the QP/QCQP hot path this package replaces")
+
+
+class SignedBoxQPFn2(Function):
+    """Box QP with the extra constraint sign(v_i) l_i <= 0.  Forward mirrors qcqp.py:99-108 (solveSignedBoxQP);
+    the reference has no backward for it (qcqp.py:111 'npt implemented', no solveDerivativesSignedBoxQP exists)."""
+
+    @staticmethod
+    def forward(ctx, P, q, l_min, l_max, v, warm_start, eps, max_iter, mu_prox=1e-7):
+        _check_box(P, q, ("l_min", l_min), ("l_max", l_max), ("v", v))
+        dev = _compute_device(P, q, l_min, l_max, v)
+        t = [_as_dev(a, dev, n) for a, n in ((P, "P"), (q, "q"), (l_min, "l_min"), (l_max, "l_max"))]
+        x = boxqp_forward(*t, eps, max_iter, mu_prox, True, v=_as_dev(v, dev, "v"))
+        return _back_to(x, q.device)
+
+    @staticmethod
+    def backward(ctx, grad_l):
+        raise NotImplementedError("SignedBoxQPFn2 has no backward in the reference either (qcqp.py:111)")

@@ -85,6 +85,16 @@ int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const 
                      double* grad_l_n, double* grad_mu, int64_t B, int32_t N, void* stream);
 
 /*
+ * Forward ADMM solve of   min 1/2 x'Px + q'x  s.t. l_min <= x <= l_max   (solveBoxQP, pybindings.cpp:32-37,
+ * Solver.cpp:198-262) and, when v != NULL, additionally sign(v_i) x_i <= 0 (solveSignedBoxQP,
+ * pybindings.cpp:47-52, Solver.cpp:374-439).  l_min, l_max, v are (B,N).  SURVEY.md 8(f) rows 1 and 3.
+ */
+int dq_boxqp_forward(const double* P, const double* q, const double* l_min, const double* l_max,
+                     const double* v, const double* warm_start, double* x, int32_t* iters, int64_t B,
+                     int32_t N, double eps, double mu_prox, int32_t max_iter, int32_t adaptative_rho,
+                     void* stream);
+
+/*
  * dq_qcqp_backward plus the two intermediate vectors the reference's per-problem binding returns
  * (pybindings.cpp:62-71): gamma (B,N/2) = dualFromPrimalQCQP and dgamma (B,N/2) = blgamma[:nc] of
  * solveDerivativesQCQP; blgamma[nc:] is -grad_q and E1 = diag(2 gamma l_n^2 mu), E2 = diag(2 gamma l_n mu^2)

@@ -206,9 +206,25 @@ void dq_oracle_set_rho_nudge(int ulps) { g_rho_nudge = ulps; }
 /* Shared skeleton of Solver::solveQP (Solver.cpp:61-123) and Solver::solveQCQP (:521-582).
  * radius == NULL selects the QP (non-negative clip, :82); otherwise the per-contact disk
  * projection prox_circle (:505-519) with radius = l_n o mu (pybindings.cpp:57). */
+static int admm_solve_box(const double* P_in, const double* q, const double* warm_start,
+                          const double* radius, const double* l_min, const double* l_max,
+                          const double* v_sign, double* x, int n, double epsilon, double mu_prox,
+                          int max_iter, int adaptative_rho);
+
 static int admm_solve(const double* P_in, const double* q, const double* warm_start,
                       const double* radius, double* x, int n, double epsilon, double mu_prox,
                       int max_iter, int adaptative_rho) {
+  return admm_solve_box(P_in, q, warm_start, radius, NULL, NULL, NULL, x, n, epsilon, mu_prox, max_iter,
+                        adaptative_rho);
+}
+
+/* l_min/l_max != NULL select the box projection of Solver::solveBoxQP (Solver.cpp:198-262, clamp at
+ * :219-220); v_sign != NULL adds the sign projection of Solver::solveSignedBoxQP (:374-439, line :398,
+ * v already passed through cwiseSign :391).  Everything else is solveQP's loop verbatim. */
+static int admm_solve_box(const double* P_in, const double* q, const double* warm_start,
+                          const double* radius, const double* l_min, const double* l_max,
+                          const double* v_sign, double* x, int n, double epsilon, double mu_prox,
+                          int max_iter, int adaptative_rho) {
   const double mu_thresh = 10., alpha_relax = 1.5, eps_rel = 1e-4; /* :64, :523-524 */
   const int is_qcqp = radius != NULL;
   double* P = dq_alloc((size_t)n * n); /* by-value copy, mutated: Solver.cpp:61,75 */
@@ -241,7 +257,16 @@ static int admm_solve(const double* P_in, const double* q, const double* warm_st
     for (int i = 0; i < n; i++) q_prox[i] = q[i] - mu_prox * l[i];  /* :81 / :540 */
     for (int i = 0; i < n; i++)                                     /* :82 / :541 */
       l_2[i] = alpha_relax * l[i] + (1 - alpha_relax) * l_2[i] + u[i] / rho;
-    if (!is_qcqp) {
+    if (l_min) {                                                    /* solveBoxQP :219-220 / solveSignedBoxQP :396-398 */
+      for (int i = 0; i < n; i++) l_2[i] = l_2[i] < l_min[i] ? l_min[i] : l_2[i]; /* cwiseMax(l_min) */
+      for (int i = 0; i < n; i++) l_2[i] = l_max[i] < l_2[i] ? l_max[i] : l_2[i]; /* cwiseMin(l_max) */
+      if (v_sign)
+        for (int i = 0; i < n; i++) {                               /* v.asDiagonal()*((v.asDiagonal()*l_2).cwiseMin(0)) */
+          double t = v_sign[i] * l_2[i];
+          t = 0 < t ? 0 : t;
+          l_2[i] = v_sign[i] * t;
+        }
+    } else if (!is_qcqp) {
       for (int i = 0; i < n; i++) l_2[i] = l_2[i] < 0 ? 0 : l_2[i]; /* cwiseMax(0) :82 */
     } else {                                                        /* prox_circle :505-519 */
       for (int c = 0; c < n / 2; c++) {
@@ -320,6 +345,24 @@ static int admm_solve(const double* P_in, const double* q, const double* warm_st
 int dq_oracle_solveQP(const double* P, const double* q, const double* warm_start, double* x,
                       int N, double eps, double mu_prox, int max_iter, int adaptative_rho) {
   return admm_solve(P, q, warm_start, NULL, x, N, eps, mu_prox, max_iter, adaptative_rho);
+}
+
+/* solveBoxQP (pybindings.cpp:32-37 -> Solver.cpp:198-262) */
+int dq_oracle_solveBoxQP(const double* P, const double* q, const double* l_min, const double* l_max,
+                         const double* warm_start, double* x, int N, double eps, double mu_prox,
+                         int max_iter, int adaptative_rho) {
+  return admm_solve_box(P, q, warm_start, NULL, l_min, l_max, NULL, x, N, eps, mu_prox, max_iter, adaptative_rho);
+}
+
+/* solveSignedBoxQP (pybindings.cpp:47-52 -> Solver.cpp:374-439); v = v.cwiseSign() (:391) */
+int dq_oracle_solveSignedBoxQP(const double* P, const double* q, const double* l_min, const double* l_max,
+                               const double* v, const double* warm_start, double* x, int N, double eps,
+                               double mu_prox, int max_iter, int adaptative_rho) {
+  double* vs = dq_alloc(N);
+  for (int i = 0; i < N; i++) vs[i] = v[i] > 0 ? 1.0 : (v[i] < 0 ? -1.0 : 0.0);
+  int it = admm_solve_box(P, q, warm_start, NULL, l_min, l_max, vs, x, N, eps, mu_prox, max_iter, adaptative_rho);
+  free(vs);
+  return it;
 }
 
 int dq_oracle_solveQCQP(const double* P, const double* q, const double* l_n, const double* mu,
@@ -488,6 +531,23 @@ void dq_oracle_qp_forward_batch(const double* P, const double* q, const double* 
   for (int64_t i = 0; i < B; i++) {
     int it = dq_oracle_solveQP(P + i * N * N, q + i * N, warm_start ? warm_start + i * N : NULL,
                                x + i * N, N, eps, mu_prox, max_iter, 1);
+    if (iters) iters[i] = it;
+  }
+}
+
+/* qcqp.py:56-66 (BoxQPFn2.forward) and :99-108 (SignedBoxQPFn2.forward); v == NULL selects the box QP */
+void dq_oracle_boxqp_forward_batch(const double* P, const double* q, const double* l_min,
+                                   const double* l_max, const double* v, double* x, int32_t* iters,
+                                   int64_t B, int N, double eps, double mu_prox, int max_iter,
+                                   int threads) {
+  int nt = pick_threads(threads);
+  (void)nt;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
+  for (int64_t i = 0; i < B; i++) {
+    int it = v ? dq_oracle_solveSignedBoxQP(P + i * N * N, q + i * N, l_min + i * N, l_max + i * N, v + i * N,
+                                            NULL, x + i * N, N, eps, mu_prox, max_iter, 1)
+               : dq_oracle_solveBoxQP(P + i * N * N, q + i * N, l_min + i * N, l_max + i * N, NULL, x + i * N,
+                                      N, eps, mu_prox, max_iter, 1);
     if (iters) iters[i] = it;
   }
 }

@@ -43,6 +43,19 @@ int dq_oracle_solveQCQP(const double* P, const double* q, const double* l_n, con
                         const double* warm_start, double* x, int N, double eps, double mu_prox,
                         int max_iter, int adaptative_rho);
 
+/* solveBoxQP (pybindings.cpp:32-37 -> Solver.cpp:198-262) and solveSignedBoxQP (pybindings.cpp:47-52 ->
+ * Solver.cpp:374-439): solveQP's loop with the box clamp (and the sign projection).  SURVEY 8(f) rows 1 and 3. */
+int dq_oracle_solveBoxQP(const double* P, const double* q, const double* l_min, const double* l_max,
+                         const double* warm_start, double* x, int N, double eps, double mu_prox,
+                         int max_iter, int adaptative_rho);
+int dq_oracle_solveSignedBoxQP(const double* P, const double* q, const double* l_min, const double* l_max,
+                               const double* v, const double* warm_start, double* x, int N, double eps,
+                               double mu_prox, int max_iter, int adaptative_rho);
+void dq_oracle_boxqp_forward_batch(const double* P, const double* q, const double* l_min,
+                                   const double* l_max, const double* v /* NULL: box only */, double* x,
+                                   int32_t* iters, int64_t B, int N, double eps, double mu_prox,
+                                   int max_iter, int threads);
+
 /* solveDerivativesQP (pybindings.cpp:24-30 -> Solver.cpp:125-196).  bl has N entries. */
 void dq_oracle_solveDerivativesQP(const double* P, const double* q, const double* l,
                                   const double* grad_l, double* bl, int N, double epsilon);

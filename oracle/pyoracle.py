@@ -78,6 +78,9 @@ def lib():
         L.dq_oracle_qcqp_backward_batch.argtypes = [_dp] * 10 + [ctypes.c_int64, ctypes.c_int,
                                                                  ctypes.c_int]
         L.dq_oracle_max_threads.restype = ctypes.c_int
+        L.dq_oracle_boxqp_forward_batch.restype = None
+        L.dq_oracle_boxqp_forward_batch.argtypes = [_dp] * 6 + [_ip, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
+                                                              ctypes.c_double, ctypes.c_int, ctypes.c_int]
         L.dq_oracle_set_ir_force.restype = None
         L.dq_oracle_set_ir_force.argtypes = [ctypes.c_int]
         L.dq_oracle_set_rho_nudge.restype = None
@@ -170,6 +173,18 @@ def qp_forward(P, q, warm_start, eps, max_iter, mu_prox=1e-7, threads=0, return_
     iters = np.zeros(B, dtype=np.int32)
     lib().dq_oracle_qp_forward_batch(_p(P), _p(q), _p(ws), _p(x), iters.ctypes.data_as(_ip), B, N,
                                      eps, mu_prox, int(max_iter), threads)
+    return (x, iters) if return_iters else x
+
+
+def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, v=None, threads=0, return_iters=False):
+    """BoxQPFn2.forward (qcqp.py:56-66) / SignedBoxQPFn2.forward (:99-108, when v is given) in one C call."""
+    P, q, lo, hi = _c(P), _c(q), _c(l_min), _c(l_max)
+    vv = None if v is None else _c(v)
+    B, N = P.shape[0], P.shape[1]
+    x = np.empty((B, N, 1))
+    iters = np.zeros(B, dtype=np.int32)
+    lib().dq_oracle_boxqp_forward_batch(_p(P), _p(q), _p(lo), _p(hi), _p(vv), _p(x), iters.ctypes.data_as(_ip), B, N,
+                                        eps, mu_prox, int(max_iter), threads)
     return (x, iters) if return_iters else x
 
 

@@ -38,6 +38,8 @@ def lib():
         L.dq_ref_qp_backward_batch.argtypes = [_dp] * 6 + [i64, i, i]
         L.dq_ref_qcqp_forward_batch.argtypes = [_dp] * 6 + [i64, i, d, d, i, i]
         L.dq_ref_qcqp_backward_batch.argtypes = [_dp] * 10 + [i64, i, i]
+        L.dq_ref_boxqp_forward_batch.argtypes = [_dp] * 6 + [i64, i, d, d, i, i]
+        L.dq_ref_boxqp_forward_batch.restype = None
         for f in ("dq_ref_solveQP", "dq_ref_solveDerivativesQP", "dq_ref_solveQCQP", "dq_ref_solveDerivativesQCQP",
                   "dq_ref_qp_forward_batch", "dq_ref_qp_backward_batch", "dq_ref_qcqp_forward_batch",
                   "dq_ref_qcqp_backward_batch"):
@@ -99,6 +101,15 @@ def qp_forward(P, q, warm_start, eps, max_iter, mu_prox=1e-7, threads=0):
     ws = None if warm_start is None else _c(warm_start)
     x = np.empty((B, N, 1))
     lib().dq_ref_qp_forward_batch(_p(P), _p(q), _p(ws), _p(x), B, N, eps, mu_prox, int(max_iter), threads)
+    return x
+
+
+def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, v=None, threads=0):
+    P, q, lo, hi = _c(P), _c(q), _c(l_min), _c(l_max)
+    vv = None if v is None else _c(v)
+    B, N = P.shape[0], P.shape[1]
+    x = np.empty((B, N, 1))
+    lib().dq_ref_boxqp_forward_batch(_p(P), _p(q), _p(lo), _p(hi), _p(vv), _p(x), B, N, eps, mu_prox, int(max_iter), threads)
     return x
 
 

@@ -58,6 +58,28 @@ void dq_ref_solveDerivativesQP(const double* P, const double* q, const double* l
   for (int i = 0; i < N; i++) bl[i] = b(i);
 }
 
+// pybindings.cpp:32-37 and :47-52 (v == nullptr: solveBoxQP, else solveSignedBoxQP)
+void dq_ref_solveBoxQP(const double* P, const double* q, const double* l_min, const double* l_max, const double* v,
+                       double* x, int N, double eps, double mu_prox, int max_iter, int adaptative_rho) {
+  Solver solver;
+  VectorXd s = v ? solver.solveSignedBoxQP(to_mat(P, N), to_vec(q, N), to_vec(l_min, N), to_vec(l_max, N), to_vec(v, N),
+                                           to_vec(nullptr, N), eps, mu_prox, max_iter, adaptative_rho != 0)
+                 : solver.solveBoxQP(to_mat(P, N), to_vec(q, N), to_vec(l_min, N), to_vec(l_max, N), to_vec(nullptr, N),
+                                     eps, mu_prox, max_iter, adaptative_rho != 0);
+  for (int i = 0; i < N; i++) x[i] = s(i);
+}
+
+void dq_ref_boxqp_forward_batch(const double* P, const double* q, const double* l_min, const double* l_max,
+                                const double* v, double* x, int64_t B, int N, double eps, double mu_prox, int max_iter,
+                                int threads) {
+  const int nt = pick_threads(threads);
+  (void)nt;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
+  for (int64_t i = 0; i < B; i++)  // qcqp.py:61-63 / :104-106
+    dq_ref_solveBoxQP(P + i * N * N, q + i * N, l_min + i * N, l_max + i * N, v ? v + i * N : nullptr, x + i * N, N, eps,
+                      mu_prox, max_iter, 1);
+}
+
 // pybindings.cpp:54-60
 void dq_ref_solveQCQP(const double* P, const double* q, const double* l_n, const double* mu, const double* ws,
                       double* x, int N, double eps, double mu_prox, int max_iter, int adaptative_rho) {

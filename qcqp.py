@@ -6,4 +6,4 @@ import torch
 
 torch.set_default_dtype(torch.double)
 
-from diffqcqp_b200.qcqp import QPFn2, QCQPFn2  # noqa: E402,F401
+from diffqcqp_b200.qcqp import QPFn2, QCQPFn2, BoxQPFn2, SignedBoxQPFn2  # noqa: E402,F401

@@ -377,3 +377,28 @@ def test_oracle_equals_live_reference_build(oracle):
     P, q = spd(r, 6), 2 * r.random(6) - 1
     assert np.array_equal(oracle.solveQP(P, q, np.zeros(6)), pyref.solveQP(P, q, np.zeros(6)))
     assert np.array_equal(oracle.solveQP(P, q, np.ones(6), 1e-7, 1e-7, 50, False), pyref.solveQP(P, q, np.ones(6), 1e-7, 1e-7, 50, False))
+
+
+def test_oracle_box_forward_equals_live_reference_build(oracle):
+    """solveBoxQP / solveSignedBoxQP restatements against the reference build, bit for bit."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref/libdq_ref.so not built (needs /root/reference)")
+    r = rng(11)
+    for n, B, eps in ((1, 9), (4, 60), (8, 200), (13, 40), (32, 12)) and ((1, 9, 1e-7), (4, 60, 1e-10), (8, 200, 1e-7), (13, 40, 1e-7), (32, 12, 1e-10)):
+        P = np.stack([spd(r, n) for _ in range(B)])
+        if n == 8:
+            P[: B // 2] = np.stack([np.diag(r.random(n)) for _ in range(B // 2)])
+        q = 2 * r.random((B, n, 1)) - 1
+        lo, hi, v = -r.random((B, n, 1)), r.random((B, n, 1)), 2 * r.random((B, n, 1)) - 1
+        x = oracle.boxqp_forward(P, q, lo, hi, eps, 1000)
+        assert np.array_equal(x, pyref.boxqp_forward(P, q, lo, hi, eps, 1000)), n
+        assert np.all(x >= lo) and np.all(x <= hi)
+        xs = oracle.boxqp_forward(P, q, lo, hi, eps, 1000, v=v)
+        assert np.array_equal(xs, pyref.boxqp_forward(P, q, lo, hi, eps, 1000, v=v)), n
+        assert np.all(np.sign(v) * xs <= 0)
+    # with the box at [0, +inf) the box QP is the QP
+    P = np.stack([spd(r, 6) for _ in range(20)])
+    q = 2 * r.random((20, 6, 1)) - 1
+    xb = oracle.boxqp_forward(P, q, np.zeros((20, 6, 1)), np.full((20, 6, 1), np.inf), 1e-7, 1000)
+    assert np.array_equal(xb, oracle.qp_forward(P, q, None, 1e-7, 1000))

@@ -592,3 +592,42 @@ def test_unbatched_layers(cuda_lib, oracle):
     assert l.shape == (n,) and np.abs(l.detach().numpy() - xo).max() <= 1e-6
     l.sum().backward()
     assert P2.grad.shape == (n, n) and q2.grad.shape == (n, 1) and l_n.grad.shape == (n // 2, 1) and mu.grad.shape == (n // 2, 1)
+
+
+# ------------------------------------------------------------------------------------ Box / SignedBox QP forward
+@pytest.mark.parametrize("N,B,eps,diag", [(8, 4099, 1e-7, True), (8, 2050, 1e-7, False), (5, 333, 1e-10, False),
+                                           (16, 1023, 1e-7, False), (32, 257, 1e-7, False), (1, 65, 1e-7, False)])
+def test_boxqp_and_signedboxqp_forward_vs_oracle(dq, wl, oracle, N, B, eps, diag):
+    """solveBoxQP (Solver.cpp:198-262) and solveSignedBoxQP (:374-439): solveQP's loop with a different projection."""
+    P, q, _ = (wl.qp_diag if diag else wl.qp_dense)(B, N, seed=200 + N)
+    g = torch.Generator().manual_seed(300 + N)
+    lo = -torch.rand(B, N, 1, generator=g, dtype=torch.float64)
+    hi = torch.rand(B, N, 1, generator=g, dtype=torch.float64)
+    v = 2 * torch.rand(B, N, 1, generator=g, dtype=torch.float64) - 1
+    v[::7, 0] = 0.0  # sign(0) = 0 pins the element to zero
+    xo, ito = oracle.boxqp_forward(P.numpy(), q.numpy(), lo.numpy(), hi.numpy(), eps, 1000, return_iters=True)
+    x, it = dq.boxqp_forward(*dev(P, q, lo, hi), eps, 1000, return_iters=True)
+    assert np.array_equal(it.cpu().numpy(), ito)
+    check_x(x, xo, eps)
+    assert torch.all(x >= lo.cuda()) and torch.all(x <= hi.cuda())
+    xo, ito = oracle.boxqp_forward(P.numpy(), q.numpy(), lo.numpy(), hi.numpy(), eps, 1000, v=v.numpy(), return_iters=True)
+    x, it = dq.boxqp_forward(*dev(P, q, lo, hi), eps, 1000, v=v.cuda(), return_iters=True)
+    assert np.array_equal(it.cpu().numpy(), ito)
+    check_x(x, xo, eps)
+    assert torch.all(torch.sign(v.cuda()) * x <= 0) and torch.all(x[::7, 0] == 0)
+
+
+def test_box_layers_surface(dq, wl, oracle):
+    import qcqp
+    P, q, _ = wl.qp_dense(40, 8, seed=210)
+    lo, hi = -torch.ones(40, 8, 1, dtype=torch.float64) * 0.3, torch.ones(40, 8, 1, dtype=torch.float64) * 0.2
+    x = qcqp.BoxQPFn2.apply(P.cuda(), q.cuda(), lo.cuda(), hi.cuda(), torch.zeros(40, 8, 1).cuda(), EPS, 1000)
+    xo = oracle.boxqp_forward(P.numpy(), q.numpy(), lo.numpy(), hi.numpy(), EPS, 1000)
+    check_x(x, xo, EPS)
+    v = torch.ones(40, 8, 1, dtype=torch.float64)
+    xs = qcqp.SignedBoxQPFn2.apply(P, q, lo, hi, v, torch.zeros(40, 8, 1), EPS, 1000)   # CPU tensors in -> CPU out
+    assert not xs.is_cuda and torch.all(xs <= 0)
+    Pg = P.cuda().requires_grad_(True)
+    xb = qcqp.BoxQPFn2.apply(Pg, q.cuda(), lo.cuda(), hi.cuda(), torch.zeros(40, 8, 1).cuda(), EPS, 1000)
+    with pytest.raises(NotImplementedError):
+        xb.sum().backward()
