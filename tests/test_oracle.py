@@ -385,7 +385,7 @@ def test_oracle_box_forward_equals_live_reference_build(oracle):
     if not pyref.available():
         pytest.skip("oracle/_ref/libdq_ref.so not built (needs /root/reference)")
     r = rng(11)
-    for n, B, eps in ((1, 9), (4, 60), (8, 200), (13, 40), (32, 12)) and ((1, 9, 1e-7), (4, 60, 1e-10), (8, 200, 1e-7), (13, 40, 1e-7), (32, 12, 1e-10)):
+    for n, B, eps in ((1, 9, 1e-7), (4, 60, 1e-10), (8, 200, 1e-7), (13, 40, 1e-7), (32, 12, 1e-10)):
         P = np.stack([spd(r, n) for _ in range(B)])
         if n == 8:
             P[: B // 2] = np.stack([np.diag(r.random(n)) for _ in range(B // 2)])
