@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("DQ_LIB_PATH") or os.path.join(_HERE, "libdiffqcqp_b20
 SYMBOLS = [
     "dq_version", "dq_build_arch", "dq_error_string", "dq_last_cuda_error", "dq_max_n",
     "dq_qp_forward", "dq_qp_backward", "dq_qcqp_forward", "dq_qcqp_backward",
-    "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release", "dq_qcqp_backward_ex", "dq_boxqp_forward",
+    "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release", "dq_qcqp_backward_ex", "dq_boxqp_forward", "dq_boxqp_backward",
 ]
 
 _vp = ctypes.c_void_p
@@ -55,6 +55,8 @@ def load():
     L.dq_qcqp_backward.argtypes = [_vp] * 10 + [_i64, _i32, _vp]
     L.dq_boxqp_forward.restype = ctypes.c_int
     L.dq_boxqp_forward.argtypes = [_vp] * 8 + [_i64, _i32, _f64, _f64, _i32, _i32, _vp]
+    L.dq_boxqp_backward.restype = ctypes.c_int
+    L.dq_boxqp_backward.argtypes = [_vp] * 10 + [_i64, _i32, _vp]
     L.dq_qcqp_backward_ex.restype = ctypes.c_int
     L.dq_qcqp_backward_ex.argtypes = [_vp] * 12 + [_i64, _i32, _vp]
     L.dq_qp_solve_host.restype = ctypes.c_int

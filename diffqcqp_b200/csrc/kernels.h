@@ -43,6 +43,22 @@ struct BwdParams {
   long long n_groups;  // ceil(B / (32/T)): one warp per group
 };
 
+struct BoxBwdParams {
+  const double* P;
+  const double* q;
+  const double* l_min;
+  const double* l_max;
+  const double* x;
+  const double* grad_x;
+  double* grad_P;      // nullable
+  double* grad_q;      // nullable
+  double* grad_l_min;  // nullable
+  double* grad_l_max;  // nullable
+  long long B;
+  int N;
+  long long n_groups;
+};
+
 // T = tile width (8, 16 or 32 lanes per problem); a warp carries 32/T problems.
 inline int tile_width(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
 
@@ -51,5 +67,6 @@ size_t fwd_smem_bytes(int T);
 cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t stream);
 cudaError_t launch_qp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, cudaStream_t stream);
+cudaError_t launch_boxqp_bwd(const BoxBwdParams& p, int T, cudaStream_t stream);
 
 }  // namespace dq

@@ -27,7 +27,7 @@ from torch.autograd import Function
 from . import _lib
 
 __all__ = ["QPFn2", "QCQPFn2", "BoxQPFn2", "SignedBoxQPFn2", "qp_forward", "qp_backward", "qcqp_forward",
-           "qcqp_backward", "boxqp_forward"]
+           "qcqp_backward", "boxqp_forward", "boxqp_backward"]
 
 
 def _ptr(t):
@@ -153,6 +153,20 @@ def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, adaptative_rh
     return (x, iters) if return_iters else x
 
 
+def boxqp_backward(P, q, l_min, l_max, x, grad_x, need=(True, True, True, True)):
+    dev = P.device
+    B, N = P.size(0), P.size(1)
+    gP = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need[0] else None
+    gq, glo, ghi = (torch.empty((B, N, 1), dtype=torch.float64, device=dev) if n else None for n in need[1:4])
+    if any(need):
+        L = _lib.load()
+        with torch.cuda.device(dev):
+            rc = L.dq_boxqp_backward(_ptr(P), _ptr(q), _ptr(l_min), _ptr(l_max), _ptr(x), _ptr(grad_x), _ptr(gP), _ptr(gq),
+                                     _ptr(glo), _ptr(ghi), B, N, _stream_ptr(dev))
+        _lib.check(rc, "dq_boxqp_backward")
+    return gP, gq, glo, ghi
+
+
 def _back_to(t, device):
     if t is None or t.device == device:
         return t
@@ -212,12 +226,11 @@ def _check_box(P, q, *bounds):
 
 
 class BoxQPFn2(Function):
-    """min 1/2 l'Pl + q'l  s.t. l_min <= l <= l_max, batched.  Forward mirrors qcqp.py:56-66 (solveBoxQP).
-
-    SURVEY.md 8(f) row 1.  The reference's Python backward for this class cannot run as shipped (it unpacks six names
-    from four values, swaps l_min/l_max when reading the saved tensors and calls a method torch does not have,
-    qcqp.py:72-93), so there is no reference behaviour to reproduce yet: backward raises until the C++
-    solveDerivativesBoxQP path (Solver.cpp:303-371) has its own kernel."""
+    """min 1/2 l'Pl + q'l  s.t. l_min <= l <= l_max, batched.  Forward mirrors qcqp.py:56-66
+    (solveBoxQP); backward is what qcqp.py:68-94 sets out to compute from solveDerivativesBoxQP -- that code cannot
+    run as shipped (it unpacks six names from four values, reads l_min/l_max swapped and calls Tensor.asDiagonal), so
+    the gradients are defined from the C++ (Solver.cpp:263-371): grad_P = -dl l', grad_q = -dl,
+    grad_l_min = -dgamma_lower gamma_lower, grad_l_max = +dgamma_upper gamma_upper (finite-difference checked)."""
 
     @staticmethod
     def forward(ctx, P, q, l_min, l_max, warm_start, eps, max_iter, mu_prox=1e-7):
@@ -225,12 +238,17 @@ class BoxQPFn2(Function):
         dev = _compute_device(P, q, l_min, l_max)
         t = [_as_dev(a, dev, n) for a, n in ((P, "P"), (q, "q"), (l_min, "l_min"), (l_max, "l_max"))]
         x = boxqp_forward(*t, eps, max_iter, mu_prox, True)
+        ctx.save_for_backward(*t, x)
+        ctx.out_device = q.device
         return _back_to(x, q.device)
 
     @staticmethod
     def backward(ctx, grad_l):
-        raise NotImplementedError("BoxQPFn2.backward: the reference's own backward does not run (qcqp.py:72-93); "
-                                  "not part of the QP/QCQP hot path this package replaces")
+        Pd, qd, lo, hi, x = ctx.saved_tensors
+        g = _as_dev(grad_l, Pd.device, "grad_l")
+        grads = boxqp_backward(Pd, qd, lo, hi, x, g, tuple(ctx.needs_input_grad[:4]))
+        o = ctx.out_device
+        return tuple(_back_to(t, o) for t in grads) + (None, None, None, None)
 
 
 class SignedBoxQPFn2(Function):

@@ -95,6 +95,16 @@ int dq_boxqp_forward(const double* P, const double* q, const double* l_min, cons
                      void* stream);
 
 /*
+ * Backward of the box QP (pybindings.cpp:39-45, Solver.cpp:263-371): gamma = dualFromPrimalBoxQP,
+ * blgamma = solveDerivativesBoxQP with epsilon = 1e-10, then grad_P = -dl x', grad_q = -dl,
+ * grad_l_min = -dgamma_lower o gamma_lower, grad_l_max = +dgamma_upper o gamma_upper (qcqp.py:86-93; the
+ * shipped Python cannot run and carries the wrong sign for l_max, see csrc/boxqp_bwd.cu).  Outputs may be NULL.
+ */
+int dq_boxqp_backward(const double* P, const double* q, const double* l_min, const double* l_max,
+                      const double* x, const double* grad_x, double* grad_P, double* grad_q,
+                      double* grad_l_min, double* grad_l_max, int64_t B, int32_t N, void* stream);
+
+/*
  * dq_qcqp_backward plus the two intermediate vectors the reference's per-problem binding returns
  * (pybindings.cpp:62-71): gamma (B,N/2) = dualFromPrimalQCQP and dgamma (B,N/2) = blgamma[:nc] of
  * solveDerivativesQCQP; blgamma[nc:] is -grad_q and E1 = diag(2 gamma l_n^2 mu), E2 = diag(2 gamma l_n mu^2)

@@ -144,10 +144,13 @@ double dq_oracle_power_iteration(const double* A, int n, int max_iter) {
 static int g_ir_force = 0;
 void dq_oracle_set_ir_force(int n) { g_ir_force = n; }
 
-int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, int m) {
+/* General form: A is R x C row-major (Solver.cpp:15 takes any Ref<const MatrixXd>; dualFromPrimalBoxQP
+ * calls it with a rectangular N x k matrix, :297).  x has C entries. */
+static int ir_rect(const double* A, int R, int C, const double* b, double* x) {
   const double mu_ir = 1e-7, epsilon = 1e-10;
   const int max_iter = 10;
   const int force = g_ir_force;
+  const int m = C;
   if (m == 0) return 0;
   double* Ab = dq_alloc(m);
   double* AA = dq_alloc((size_t)m * m);
@@ -158,13 +161,13 @@ int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, 
   double* delta = dq_alloc(m);
   for (int i = 0; i < m; i++) { /* Ab = A^T b  :19 */
     double s = 0.0;
-    for (int k = 0; k < m; k++) s += A[k * m + i] * b[k];
+    for (int k = 0; k < R; k++) s += A[k * m + i] * b[k];
     Ab[i] = s;
   }
   for (int i = 0; i < m; i++) /* AA = A^T A  :20 */
     for (int j = 0; j < m; j++) {
       double s = 0.0;
-      for (int k = 0; k < m; k++) s += A[k * m + i] * A[k * m + j];
+      for (int k = 0; k < R; k++) s += A[k * m + i] * A[k * m + j];
       AA[i * m + j] = s;
     }
   for (int i = 0; i < m; i++) AA[i * m + i] += mu_ir; /* :21 */
@@ -193,6 +196,10 @@ int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, 
   }
   free(Ab); free(AA); free(AAinv); free(work); free(w); free(t); free(delta);
   return it;
+}
+
+int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, int m) {
+  return ir_rect(A, m, m, b, x);
 }
 
 /* Test hook (not in the reference): move the initial rho by this many ulps.  pow() is libm-dependent
@@ -499,6 +506,71 @@ void dq_oracle_solveDerivativesQCQP(const double* P, const double* q, const doub
   free(mul_n); free(gamma); free(slack); free(not_null); free(A); free(dd); free(b);
 }
 
+/* ------------------------------------------------------------ Box QP backward ------------- */
+/* pybindings.cpp:39-45: gamma = dualFromPrimalBoxQP(P,q,l_min,l_max,l,epsilon) (Solver.cpp:263-301, its
+ * debug print of the active indices :286-288 omitted), blgamma = solveDerivativesBoxQP(...) (:303-371).
+ * gamma has 2N entries [lower ; upper], blgamma 3N entries [dgamma_lower ; dgamma_upper ; dl]. */
+static int box_active(const double* l, const double* l_min, const double* l_max, int N, double epsilon,
+                      int* not_null) {
+  int k = 0;
+  for (int i = 0; i < N; i++) {                 /* :268-283 / :307-320: lower then upper, element by element */
+    if (!(l[i] - l_min[i] > epsilon)) not_null[k++] = i;
+    if (!(l[i] - l_max[i] < -epsilon)) not_null[k++] = N + i;
+  }
+  return k;
+}
+
+void dq_oracle_solveDerivativesBoxQP(const double* P, const double* q, const double* l_min,
+                                     const double* l_max, const double* l, const double* grad_l,
+                                     double* blgamma, double* gamma, int N, double epsilon) {
+  int* not_null = (int*)malloc((2 * N + 1) * sizeof(int));
+  int k = box_active(l, l_min, l_max, N, epsilon, not_null);
+  /* ---- dualFromPrimalBoxQP: gamma_nn = IR(Id2, -P l - q), Id2 is N x k with -1 (lower) / +1 (upper)  :290-300 */
+  double* Id2 = dq_alloc((size_t)N * (k ? k : 1));
+  double* r = dq_alloc(N);
+  double* gnn = dq_alloc(k ? k : 1);
+  for (int i = 0; i < N * k; i++) Id2[i] = 0.0;
+  for (int j = 0; j < k; j++) {
+    if (not_null[j] < N) Id2[not_null[j] * k + j] = -1;
+    else Id2[(not_null[j] - N) * k + j] = 1;
+  }
+  gemv(P, l, r, N);
+  for (int i = 0; i < N; i++) r[i] = -r[i] - q[i];           /* -P*l - q */
+  ir_rect(Id2, N, k, r, gnn);
+  for (int i = 0; i < 2 * N; i++) gamma[i] = 0.0;
+  for (int j = 0; j < k; j++) gamma[not_null[j]] = gnn[j];
+  /* ---- solveDerivativesBoxQP: G = [[0, B],[Id2, P]], B(j,:) = gamma_j Id2(:,j)^T, A = G^T  :329-346 */
+  int m = k + N;
+  double* A = dq_alloc((size_t)m * m);
+  double* dd = dq_alloc(m);
+  double* b = dq_alloc(m);
+  for (int i = 0; i < m * m; i++) A[i] = 0.0;
+  for (int j = 0; j < k; j++)
+    for (int i = 0; i < N; i++) {
+      A[(k + i) * m + j] = gamma[not_null[j]] * Id2[i * k + j]; /* G(j, k+i) = B(j,i); transposed */
+      A[j * m + (k + i)] = Id2[i * k + j];                      /* G(k+i, j) = Id2(i,j); transposed */
+    }
+  for (int rr = 0; rr < N; rr++)
+    for (int c = 0; c < N; c++) A[(k + c) * m + (k + rr)] = P[rr * N + c]; /* G(k+r, k+c) = P(r,c); transposed */
+  for (int i = 0; i < m; i++) dd[i] = i < k ? 0. : grad_l[i - k];          /* :347-355 */
+  ir_rect(A, m, m, dd, b);                                                  /* :357 */
+  for (int i = 0; i < 3 * N; i++) blgamma[i] = 0.0;
+  for (int j = 0; j < k; j++) blgamma[not_null[j]] = b[j];                  /* :359-361 */
+  for (int i = 0; i < N; i++) blgamma[2 * N + i] = b[k + i];                /* :362-364 */
+  free(not_null); free(Id2); free(r); free(gnn); free(A); free(dd); free(b);
+}
+
+/* BoxQPFn2.backward as qcqp.py:68-94 evidently intends it (the shipped code cannot run: it unpacks six names
+ * from four values :78, reads the saved l_min/l_max swapped :72 and calls Tensor.asDiagonal :91,93):
+ * dl = blgamma[2N:], dgamma = blgamma[:2N];  grad_P = -dl l^T, grad_q = -dl,
+ * grad_l_min = -dgamma_lower o gamma_lower (:91), grad_l_max = +dgamma_upper o gamma_upper: line :93 has a
+ * minus, which finite differences refute (tests/test_oracle.py) and the C++ side's own l_min_max(i+N) =
+ * -l_max(i) (Solver.cpp:322) contradicts; since that Python never ran there is no behaviour to preserve. */
+void dq_oracle_boxqp_backward_batch(const double* P, const double* q, const double* l_min,
+                                    const double* l_max, const double* x, const double* grad_x,
+                                    double* grad_P, double* grad_q, double* grad_l_min,
+                                    double* grad_l_max, int64_t B, int N, int threads);
+
 /* ------------------------------------------------------------ batched: qcqp.py ----------- */
 int dq_oracle_max_threads(void) {
 #ifdef _OPENMP
@@ -549,6 +621,31 @@ void dq_oracle_boxqp_forward_batch(const double* P, const double* q, const doubl
                : dq_oracle_solveBoxQP(P + i * N * N, q + i * N, l_min + i * N, l_max + i * N, NULL, x + i * N,
                                       N, eps, mu_prox, max_iter, 1);
     if (iters) iters[i] = it;
+  }
+}
+
+void dq_oracle_boxqp_backward_batch(const double* P, const double* q, const double* l_min,
+                                    const double* l_max, const double* x, const double* grad_x,
+                                    double* grad_P, double* grad_q, double* grad_l_min,
+                                    double* grad_l_max, int64_t B, int N, int threads) {
+  int nt = pick_threads(threads);
+  (void)nt;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
+  for (int64_t i = 0; i < B; i++) {
+    double* blg = dq_alloc(3 * N);
+    double* gam = dq_alloc(2 * N);
+    dq_oracle_solveDerivativesBoxQP(P + i * N * N, q + i * N, l_min + i * N, l_max + i * N, x + i * N,
+                                    grad_x + i * N, blg, gam, N, 1e-10);
+    const double* dl = blg + 2 * N;
+    if (grad_P)
+      for (int r = 0; r < N; r++)
+        for (int c = 0; c < N; c++) grad_P[i * N * N + r * N + c] = -(dl[r] * x[i * N + c]);
+    for (int r = 0; r < N; r++) {
+      if (grad_q) grad_q[i * N + r] = -dl[r];
+      if (grad_l_min) grad_l_min[i * N + r] = -(blg[r] * gam[r]);
+      if (grad_l_max) grad_l_max[i * N + r] = blg[N + r] * gam[N + r];  /* sign fixed, see the note above */
+    }
+    free(blg); free(gam);
   }
 }
 

@@ -56,6 +56,16 @@ void dq_oracle_boxqp_forward_batch(const double* P, const double* q, const doubl
                                    int32_t* iters, int64_t B, int N, double eps, double mu_prox,
                                    int max_iter, int threads);
 
+/* solveDerivativesBoxQP (pybindings.cpp:39-45 -> Solver.cpp:263-371): gamma (2N) = dualFromPrimalBoxQP,
+ * blgamma (3N) = [dgamma_lower ; dgamma_upper ; dl]. */
+void dq_oracle_solveDerivativesBoxQP(const double* P, const double* q, const double* l_min,
+                                     const double* l_max, const double* l, const double* grad_l,
+                                     double* blgamma, double* gamma, int N, double epsilon);
+void dq_oracle_boxqp_backward_batch(const double* P, const double* q, const double* l_min,
+                                    const double* l_max, const double* x, const double* grad_x,
+                                    double* grad_P, double* grad_q, double* grad_l_min,
+                                    double* grad_l_max, int64_t B, int N, int threads);
+
 /* solveDerivativesQP (pybindings.cpp:24-30 -> Solver.cpp:125-196).  bl has N entries. */
 void dq_oracle_solveDerivativesQP(const double* P, const double* q, const double* l,
                                   const double* grad_l, double* bl, int N, double epsilon);

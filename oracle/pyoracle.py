@@ -78,6 +78,10 @@ def lib():
         L.dq_oracle_qcqp_backward_batch.argtypes = [_dp] * 10 + [ctypes.c_int64, ctypes.c_int,
                                                                  ctypes.c_int]
         L.dq_oracle_max_threads.restype = ctypes.c_int
+        L.dq_oracle_boxqp_backward_batch.restype = None
+        L.dq_oracle_boxqp_backward_batch.argtypes = [_dp] * 10 + [ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+        L.dq_oracle_solveDerivativesBoxQP.restype = None
+        L.dq_oracle_solveDerivativesBoxQP.argtypes = [_dp] * 8 + [ctypes.c_int, ctypes.c_double]
         L.dq_oracle_boxqp_forward_batch.restype = None
         L.dq_oracle_boxqp_forward_batch.argtypes = [_dp] * 6 + [_ip, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                                               ctypes.c_double, ctypes.c_int, ctypes.c_int]
@@ -186,6 +190,26 @@ def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, v=None, threa
     lib().dq_oracle_boxqp_forward_batch(_p(P), _p(q), _p(lo), _p(hi), _p(vv), _p(x), iters.ctypes.data_as(_ip), B, N,
                                         eps, mu_prox, int(max_iter), threads)
     return (x, iters) if return_iters else x
+
+
+def boxqp_backward(P, q, l_min, l_max, x, grad_x, threads=0):
+    """BoxQPFn2.backward as qcqp.py:68-94 intends it -> (grad_P, grad_q, grad_l_min, grad_l_max)."""
+    P, q, lo, hi, x, g = _c(P), _c(q), _c(l_min), _c(l_max), _c(x), _c(grad_x)
+    B, N = P.shape[0], P.shape[1]
+    gP, gq, glo, ghi = np.empty((B, N, N)), np.empty((B, N, 1)), np.empty((B, N, 1)), np.empty((B, N, 1))
+    lib().dq_oracle_boxqp_backward_batch(_p(P), _p(q), _p(lo), _p(hi), _p(x), _p(g), _p(gP), _p(gq), _p(glo), _p(ghi),
+                                         B, N, threads)
+    return gP, gq, glo, ghi
+
+
+def solveDerivativesBoxQP(P, q, l_min, l_max, l, grad_l, epsilon=1e-10):
+    """pybindings.cpp:39-45 -> (blgamma (3N,), gamma (2N,))."""
+    P, q, l, g = _c(P), _c(q).reshape(-1), _c(l).reshape(-1), _c(grad_l).reshape(-1)
+    lo, hi = _c(l_min).reshape(-1), _c(l_max).reshape(-1)
+    n = q.shape[0]
+    blg, gam = np.empty(3 * n), np.empty(2 * n)
+    lib().dq_oracle_solveDerivativesBoxQP(_p(P), _p(q), _p(lo), _p(hi), _p(l), _p(g), _p(blg), _p(gam), n, epsilon)
+    return blg, gam
 
 
 def qp_backward(P, q, x, grad_x, threads=0, need_P=True, need_q=True):

@@ -38,6 +38,8 @@ def lib():
         L.dq_ref_qp_backward_batch.argtypes = [_dp] * 6 + [i64, i, i]
         L.dq_ref_qcqp_forward_batch.argtypes = [_dp] * 6 + [i64, i, d, d, i, i]
         L.dq_ref_qcqp_backward_batch.argtypes = [_dp] * 10 + [i64, i, i]
+        L.dq_ref_boxqp_backward_batch.argtypes = [_dp] * 10 + [i64, i, i]
+        L.dq_ref_boxqp_backward_batch.restype = None
         L.dq_ref_boxqp_forward_batch.argtypes = [_dp] * 6 + [i64, i, d, d, i, i]
         L.dq_ref_boxqp_forward_batch.restype = None
         for f in ("dq_ref_solveQP", "dq_ref_solveDerivativesQP", "dq_ref_solveQCQP", "dq_ref_solveDerivativesQCQP",
@@ -111,6 +113,15 @@ def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, v=None, threa
     x = np.empty((B, N, 1))
     lib().dq_ref_boxqp_forward_batch(_p(P), _p(q), _p(lo), _p(hi), _p(vv), _p(x), B, N, eps, mu_prox, int(max_iter), threads)
     return x
+
+
+def boxqp_backward(P, q, l_min, l_max, x, grad_x, threads=0):
+    P, q, lo, hi, x, g = _c(P), _c(q), _c(l_min), _c(l_max), _c(x), _c(grad_x)
+    B, N = P.shape[0], P.shape[1]
+    gP, gq, glo, ghi = np.empty((B, N, N)), np.empty((B, N, 1)), np.empty((B, N, 1)), np.empty((B, N, 1))
+    lib().dq_ref_boxqp_backward_batch(_p(P), _p(q), _p(lo), _p(hi), _p(x), _p(g), _p(gP), _p(gq), _p(glo), _p(ghi), B, N,
+                                      threads)
+    return gP, gq, glo, ghi
 
 
 def qp_backward(P, q, x, grad_x, threads=0):

@@ -6,6 +6,8 @@
 // without pybind11's Eigen casters) and the per-item loops + post-processing of qcqp.py:22-52,
 // :141-181.  Matrices arrive row-major exactly as pybind11's EigenDRef sees a C-order numpy array.
 #include <cstdint>
+#include <iostream>
+#include <vector>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -78,6 +80,42 @@ void dq_ref_boxqp_forward_batch(const double* P, const double* q, const double* 
   for (int64_t i = 0; i < B; i++)  // qcqp.py:61-63 / :104-106
     dq_ref_solveBoxQP(P + i * N * N, q + i * N, l_min + i * N, l_max + i * N, v ? v + i * N : nullptr, x + i * N, N, eps,
                       mu_prox, max_iter, 1);
+}
+
+// pybindings.cpp:39-45.  dualFromPrimalBoxQP prints the active indices to std::cout (Solver.cpp:286-288, a debug
+// leftover); the stream is muted around the call so that a batch does not flood stdout.
+void dq_ref_solveDerivativesBoxQP(const double* P, const double* q, const double* l_min, const double* l_max,
+                                  const double* l, const double* grad_l, double* blgamma, double* gamma, int N,
+                                  double epsilon) {
+  Solver solver;
+  MatrixXd Pm = to_mat(P, N);
+  VectorXd qv = to_vec(q, N), lo = to_vec(l_min, N), hi = to_vec(l_max, N), lv = to_vec(l, N), gv = to_vec(grad_l, N);
+  VectorXd gam = solver.dualFromPrimalBoxQP(Pm, qv, lo, hi, lv, epsilon);
+  VectorXd blg = solver.solveDerivativesBoxQP(Pm, qv, lo, hi, lv, gam, gv, epsilon);
+  for (int i = 0; i < 2 * N; i++) gamma[i] = gam(i);
+  for (int i = 0; i < 3 * N; i++) blgamma[i] = blg(i);
+}
+
+void dq_ref_boxqp_backward_batch(const double* P, const double* q, const double* l_min, const double* l_max,
+                                 const double* x, const double* grad_x, double* grad_P, double* grad_q,
+                                 double* grad_l_min, double* grad_l_max, int64_t B, int N, int threads) {
+  (void)threads;  // serial: std::cout's state is process-wide
+  std::cout.setstate(std::ios_base::failbit);
+  for (int64_t i = 0; i < B; i++) {  // qcqp.py:79-93 as intended (see oracle/dq_oracle.c)
+    std::vector<double> blg(3 * N), gam(2 * N);
+    dq_ref_solveDerivativesBoxQP(P + i * N * N, q + i * N, l_min + i * N, l_max + i * N, x + i * N, grad_x + i * N,
+                                 blg.data(), gam.data(), N, 1e-10);
+    const double* dl = blg.data() + 2 * N;
+    if (grad_P)
+      for (int r = 0; r < N; r++)
+        for (int c = 0; c < N; c++) grad_P[i * N * N + r * N + c] = -(dl[r] * x[i * N + c]);
+    for (int r = 0; r < N; r++) {
+      if (grad_q) grad_q[i * N + r] = -dl[r];
+      if (grad_l_min) grad_l_min[i * N + r] = -(blg[r] * gam[r]);
+      if (grad_l_max) grad_l_max[i * N + r] = blg[N + r] * gam[N + r];  // sign fixed (see oracle/dq_oracle.c)
+    }
+  }
+  std::cout.clear();
 }
 
 // pybindings.cpp:54-60

@@ -15,7 +15,7 @@ for N, B in ((8, 37), (5, 9), (16, 10), (24, 5), (32, 3)):
     Pd, qd, gd = P.cuda(), q.cuda(), g.cuda()
     run(f"qp dense N={N}", lambda: dq.qp_backward(Pd, qd, dq.qp_forward(Pd, qd, 1e-7, 200), gd))
     lo, hi, v = -torch.rand_like(qd), torch.rand_like(qd), torch.randn_like(qd)
-    run(f"box N={N}", lambda: dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200))
+    run(f"box N={N}", lambda: dq.boxqp_backward(Pd, qd, lo, hi, dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200), gd))
     run(f"signed box N={N}", lambda: dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200, v=v))
 P, q, g = wl.qp_diag(70, 8, seed=1)
 run("qp diag N=8", lambda: dq.qp_backward(P.cuda(), q.cuda(), dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 500), g.cuda()))

@@ -402,3 +402,35 @@ def test_oracle_box_forward_equals_live_reference_build(oracle):
     q = 2 * r.random((20, 6, 1)) - 1
     xb = oracle.boxqp_forward(P, q, np.zeros((20, 6, 1)), np.full((20, 6, 1), np.inf), 1e-7, 1000)
     assert np.array_equal(xb, oracle.qp_forward(P, q, None, 1e-7, 1000))
+
+
+def test_oracle_box_backward(oracle):
+    """solveDerivativesBoxQP restatement: bit-identical to the reference build away from degenerate boxes, and its
+    gradients (with the documented sign for l_max) agree with central finite differences."""
+    from oracle import pyref
+    r = rng(12)
+    if pyref.available():
+        for n, B in ((1, 7), (4, 50), (8, 150), (13, 30), (32, 8)):
+            P = np.stack([spd(r, n) for _ in range(B)])
+            q, g = 2 * r.random((B, n, 1)) - 1, 2 * r.random((B, n, 1)) - 1
+            lo, hi = -0.3 * r.random((B, n, 1)), 0.3 * r.random((B, n, 1))
+            x = oracle.boxqp_forward(P, q, lo, hi, 1e-7, 1000)
+            for a, b in zip(oracle.boxqp_backward(P, q, lo, hi, x, g), pyref.boxqp_backward(P, q, lo, hi, x, g)):
+                assert np.array_equal(a, b), n
+    n = 5
+    P = spd(r, n)[None]
+    q, g = 2 * r.random((1, n, 1)) - 1, 2 * r.random((1, n, 1)) - 1
+    lo, hi = -0.2 * np.ones((1, n, 1)), 0.25 * np.ones((1, n, 1))
+    f = lambda P, q, lo, hi: float((oracle.boxqp_forward(P, q, lo, hi, 1e-13, 50000) * g).sum())
+    x = oracle.boxqp_forward(P, q, lo, hi, 1e-13, 50000)
+    assert np.any(x <= lo + 1e-9) or np.any(x >= hi - 1e-9)
+    gP, gq, glo, ghi = oracle.boxqp_backward(P, q, lo, hi, x, g)
+    d = 1e-6
+    for which, grad in ((1, gq), (2, glo), (3, ghi)):
+        for i in range(n):
+            args = [P.copy(), q.copy(), lo.copy(), hi.copy()]
+            args[which][0, i, 0] += d
+            up = f(*args)
+            args[which][0, i, 0] -= 2 * d
+            num = (up - f(*args)) / (2 * d)
+            assert abs(num - grad[0, i, 0]) <= 2e-4 * max(1.0, abs(num)), (which, i, num, grad[0, i, 0])

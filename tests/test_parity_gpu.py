@@ -627,7 +627,45 @@ def test_box_layers_surface(dq, wl, oracle):
     v = torch.ones(40, 8, 1, dtype=torch.float64)
     xs = qcqp.SignedBoxQPFn2.apply(P, q, lo, hi, v, torch.zeros(40, 8, 1), EPS, 1000)   # CPU tensors in -> CPU out
     assert not xs.is_cuda and torch.all(xs <= 0)
+    leaves = [t.cuda().requires_grad_(True) for t in (P, q, lo, hi)]
+    xb = qcqp.BoxQPFn2.apply(*leaves, torch.zeros(40, 8, 1).cuda(), EPS, 1000)
+    xb.sum().backward()
+    for t in leaves:
+        assert t.grad is not None and t.grad.shape == t.shape and torch.all(torch.isfinite(t.grad))
     Pg = P.cuda().requires_grad_(True)
-    xb = qcqp.BoxQPFn2.apply(Pg, q.cuda(), lo.cuda(), hi.cuda(), torch.zeros(40, 8, 1).cuda(), EPS, 1000)
-    with pytest.raises(NotImplementedError):
-        xb.sum().backward()
+    xs = qcqp.SignedBoxQPFn2.apply(Pg, q.cuda(), lo.cuda(), hi.cuda(), v.cuda(), torch.zeros(40, 8, 1).cuda(), EPS, 1000)
+    with pytest.raises(NotImplementedError):  # the reference has no backward for it either (qcqp.py:111)
+        xs.sum().backward()
+
+
+@pytest.mark.parametrize("N,B,seed,diag", [(8, 2048, 400, False), (8, 1024, 401, True), (5, 333, 402, False),
+                                            (16, 512, 403, False), (24, 200, 404, False), (32, 150, 405, False), (1, 40, 406, False)])
+def test_boxqp_backward_vs_oracle(dq, wl, oracle, N, B, seed, diag):
+    """solveDerivativesBoxQP (Solver.cpp:263-371) against the oracle restatement (bit-identical to the reference
+    build on the CPU side).  Same bar as the QCQP backward: every GPU gradient row matches one of the oracle's
+    refinement iterates (the reference's stop rule is decided by rounding noise)."""
+    P, q, g = (wl.qp_diag if diag else wl.qp_dense)(B, N, seed=seed)
+    gen = torch.Generator().manual_seed(seed)
+    lo = -0.5 * torch.rand(B, N, 1, generator=gen, dtype=torch.float64)
+    hi = 0.5 * torch.rand(B, N, 1, generator=gen, dtype=torch.float64)
+    a = [t.numpy() for t in (P, q, lo, hi)]
+    xo = oracle.boxqp_forward(*a, EPS, 1000)
+    go = oracle.boxqp_backward(*a, xo, g.numpy())
+    cands = []
+    try:
+        for k in (1, 2, 3, 4, 5):
+            oracle.set_ir_force(k)
+            cands.append(oracle.boxqp_backward(*a, xo, g.numpy()))
+    finally:
+        oracle.set_ir_force(0)
+    gg = dq.boxqp_backward(*dev(P, q, lo, hi), torch.from_numpy(xo).cuda(), g.cuda())
+    for i, name in enumerate(("grad_P", "grad_q", "grad_l_min", "grad_l_max")):
+        got = gg[i].cpu().numpy()
+        assert np.all(np.isfinite(got)), name
+        scale = np.abs(go[1]).reshape(B, -1).max(1) + 1e-300           # rows are compared on the scale of dl
+        d_all = np.stack([np.abs(got - c[i]).reshape(B, -1).max(1) / scale for c in cands])
+        d_best = d_all.min(0)
+        assert d_best.max() <= 1e-5, (name, d_best.max())
+        assert np.percentile(d_best, 99) <= 1e-7, (name, np.percentile(d_best, 99))
+        d_def = np.abs(got - go[i]).reshape(B, -1).max(1) / scale
+        assert np.median(d_def) <= 1e-8, (name, np.median(d_def))
