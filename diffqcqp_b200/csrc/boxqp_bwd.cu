@@ -20,8 +20,8 @@
 // Signs.  The reference's Python backward cannot run (qcqp.py:72,78,91,93) so there is no behaviour to copy; this
 // kernel returns what that code evidently computes for grad_P, grad_q, grad_l_min (= -dgamma_lo gamma_lo) and the
 // finite-difference-correct sign for grad_l_max (= +dgamma_up gamma_up; the shipped line has a minus that the
-// C++ side's own convention, l_min_max(i+N) = -l_max(i) at Solver.cpp:322, contradicts).  oracle/dq_oracle.c
-// restates the C++ (bit-identical to the reference build) and applies the same post-processing.
+// C++ side's own convention, l_min_max(i+N) = -l_max(i) at Solver.cpp:322, contradicts).  The parity tests
+// hold a CPU restatement of that C++ (bit-identical to the reference build) with the same post-processing.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -35,7 +35,7 @@ struct BwdBoxSmem {
   static constexpr size_t bytes = (size_t)WARPS * per_warp_doubles * sizeof(double);
 };
 
-// 2 x 2 SPD inverse with the oracle's (Eigen's) operation order: unblocked LLT, then forward / backward
+// 2 x 2 SPD inverse with the reference's (Eigen's) operation order: unblocked LLT, then forward / backward
 // substitution against the identity multiplying by reciprocal pivots.  Returns the full (not symmetrised) inverse.
 struct Inv2 {
   double l00, l10, l11, r0, r1;  // Cholesky factor and reciprocal pivots
