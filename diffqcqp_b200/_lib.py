@@ -17,6 +17,7 @@ SYMBOLS = [
     "dq_version", "dq_build_arch", "dq_error_string", "dq_last_cuda_error", "dq_max_n",
     "dq_qp_forward", "dq_qp_backward", "dq_qcqp_forward", "dq_qcqp_backward",
     "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release", "dq_qcqp_backward_ex", "dq_boxqp_forward", "dq_boxqp_backward",
+    "dq_set_forward_path",
 ]
 
 _vp = ctypes.c_void_p
@@ -45,6 +46,8 @@ def load():
     L.dq_last_cuda_error.restype = ctypes.c_int
     L.dq_max_n.restype = ctypes.c_int
     L.dq_launch_count.restype = _i64
+    L.dq_set_forward_path.restype = ctypes.c_int
+    L.dq_set_forward_path.argtypes = [ctypes.c_int]
     L.dq_qp_forward.restype = ctypes.c_int
     L.dq_qp_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _f64, _i32, _i32, _vp]
     L.dq_qp_backward.restype = ctypes.c_int

@@ -350,6 +350,7 @@ int dq_max_n(void) { return DQ_MAX_N; }
 int dq_last_cuda_error(void) { return g_last_cuda_error; }
 int64_t dq_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 void dq_host_release(void) { host_release_all(); }
+int dq_set_forward_path(int path) { return dq::set_fwd_path(path == 1 ? 1 : 0); }
 
 const char* dq_error_string(int code) {
   switch (code) {

@@ -65,6 +65,7 @@ inline int tile_width(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
 size_t fwd_smem_bytes(int T);
 // prox: 0 = x >= 0 (solveQP), 1 = per-contact disks (solveQCQP), 2 = box (solveBoxQP), 3 = box + sign (solveSignedBoxQP)
 cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t stream);
+int set_fwd_path(int path);  // 0 = automatic, 1 = generic kernel only; returns the previous value
 cudaError_t launch_qp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_boxqp_bwd(const BoxBwdParams& p, int T, cudaStream_t stream);

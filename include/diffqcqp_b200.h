@@ -138,6 +138,13 @@ void dq_host_release(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t dq_launch_count(void);
 
+/*
+ * Forward kernel selection (process-wide; for tests and A/B timing).  0 = automatic: N == 8 with a 32-byte aligned
+ * P runs the persistent-warp kernel (diagonal batches on refilled tile slots), everything else the generic kernel.
+ * 1 = generic kernel only.  Both produce bit-identical results.  Returns the previous setting.
+ */
+int dq_set_forward_path(int path);
+
 #ifdef __cplusplus
 }
 #endif

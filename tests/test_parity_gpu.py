@@ -669,3 +669,72 @@ def test_boxqp_backward_vs_oracle(dq, wl, oracle, N, B, seed, diag):
         assert np.percentile(d_best, 99) <= 1e-7, (name, np.percentile(d_best, 99))
         d_def = np.abs(got - go[i]).reshape(B, -1).max(1) / scale
         assert np.median(d_def) <= 1e-8, (name, np.median(d_def))
+
+
+# ------------------------------------------------------------------------------------ the two forward kernels agree bit for bit
+@pytest.mark.parametrize("B", [1, 3, 4, 5, 17, 63, 64, 65, 1000, 4099, 20011, 65536, 150001])
+def test_forward_paths_bit_identical_qp(dq, wl, cuda_lib, B):
+    """N == 8: the persistent-warp kernel (diagonal batches on refilled tile slots) against the
+    generic kernel: same x* bits, same iteration counts, for every batch size around the chunk / batch boundaries."""
+    P, q, _ = wl.qp_diag(B, 8, seed=500 + B % 97)
+    Pd, qd = dev(P, q)
+    try:
+        cuda_lib.dq_set_forward_path(1)
+        x1, it1 = dq.qp_forward(Pd, qd, EPS, 1000, return_iters=True)
+        cuda_lib.dq_set_forward_path(0)
+        x0, it0 = dq.qp_forward(Pd, qd, EPS, 1000, return_iters=True)
+    finally:
+        cuda_lib.dq_set_forward_path(0)
+    assert torch.equal(it0, it1)
+    assert torch.equal(x0.view(torch.int64), x1.view(torch.int64))
+
+
+def test_forward_paths_bit_identical_variants(dq, wl, cuda_lib):
+    """Same comparison for the other prox variants, a batch that mixes diagonal and dense problems (dense batches of
+    the persistent kernel go through the generic group routine), tight eps, small max_iter, adaptative_rho off."""
+    B = 5003
+    g = torch.Generator().manual_seed(77)
+    P, q, _ = wl.qp_diag(B, 8, seed=600)
+    Pm = P.clone()
+    Pd_, _, _ = wl.qp_dense(B, 8, seed=601)
+    Pm[100:140] = Pd_[100:140]          # a run of dense problems across batch boundaries
+    Pm[2500] = Pd_[2500]                # a single dense problem
+    Pm[B - 1] = Pd_[B - 1]
+    lo = -torch.rand(B, 8, 1, generator=g, dtype=torch.float64)
+    hi = torch.rand(B, 8, 1, generator=g, dtype=torch.float64)
+    v = 2 * torch.rand(B, 8, 1, generator=g, dtype=torch.float64) - 1
+    Pq, qq, l_n, mu, _ = wl.qcqp_diag(B, 8, seed=602)
+    Pqm = Pq.clone()
+    Pqm[300:333] = Pd_[300:333]
+
+    def both(label, fn):
+        try:
+            cuda_lib.dq_set_forward_path(1)
+            a = fn()
+            cuda_lib.dq_set_forward_path(0)
+            b = fn()
+        finally:
+            cuda_lib.dq_set_forward_path(0)
+        bad = (a[1] != b[1]).nonzero().flatten()
+        assert bad.numel() == 0, (label, "iteration counts differ at", bad[:8].tolist())
+        if label.startswith("mixed"):
+            # A diagonal problem that shares a warp (generic kernel: groups of 4) or a batch (persistent kernel: up to 16)
+            # with a dense one is solved with the dense arithmetic (Cholesky-based inverse): which neighbours it has
+            # differs between the kernels, so those few problems agree to rounding, everything else bit for bit.
+            d = (a[0] - b[0]).abs().flatten(1).max(1)[0]
+            assert float(d.max()) <= 1e-9 * max(1.0, float(a[0].abs().max())), (label, float(d.max()))
+            assert int((d > 0).sum()) <= 64, (label, int((d > 0).sum()))
+            return
+        bad = (a[0].view(torch.int64) != b[0].view(torch.int64)).any(1).flatten().nonzero().flatten()
+        assert bad.numel() == 0, (label, "x differs at problems", bad[:8].tolist(), bad.numel())
+
+    for name, PP in (("diag", P), ("mixed", Pm)):
+        both(name + " qp eps=1e-10", lambda: dq.qp_forward(*dev(PP, q), 1e-10, 1000, return_iters=True))
+        both(name + " qp max_iter=7", lambda: dq.qp_forward(*dev(PP, q), 1e-7, 7, return_iters=True))
+        both(name + " qp max_iter=0", lambda: dq.qp_forward(*dev(PP, q), 1e-7, 0, return_iters=True))
+        both(name + " qp fixed rho", lambda: dq.qp_forward(*dev(PP, q), 1e-7, 1000, adaptative_rho=False, return_iters=True))
+        both(name + " box", lambda: dq.boxqp_forward(*dev(PP, q, lo, hi), 1e-7, 1000, return_iters=True))
+        both(name + " signed box", lambda: dq.boxqp_forward(*dev(PP, q, lo, hi), 1e-7, 1000, v=v.cuda(), return_iters=True))
+    for name, PP in (("diag", Pq), ("mixed", Pqm)):
+        both(name + " qcqp", lambda: dq.qcqp_forward(*dev(PP, qq, l_n, mu), 1e-7, 1000, return_iters=True))
+        both(name + " qcqp eps=1e-10", lambda: dq.qcqp_forward(*dev(PP, qq, l_n, mu), 1e-10, 1000, return_iters=True))
