@@ -428,28 +428,29 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : 16) / FWD_WARPS
 
 
 // =====================================================================================================
-// Diagonal fast path for N == 8 (the headline shape): persistent warps, batched set-up, refilled tile slots.
+// Diagonal fast path for N == 8 (the headline shape): persistent CTAs, batched set-up, refilled tile slots.
 //
 // The generic kernel gives a warp four problems and runs until the slowest of them stops (mean 36 loop trips for
 // problems that need 24 on average), pays the set-up (power iteration, pow) once per four problems with a
 // DRAM-latency stall in front, and leaves the one 500-iteration problem of a batch to finish alone after
-// everything else has drained.  Here a warp owns a contiguous chunk of the batch and walks it in batches of up
-// to 16 problems:
+// everything else has drained.  Here a CTA of DIAG_WARPS warps owns a contiguous chunk of the batch and walks it in
+// batches of up to 16 problems per warp:
 //   1. P is read as one flat, fully coalesced stream (256-bit loads, two problems per instruction); only the
 //      diagonal is kept (shared-memory record), the off-diagonal entries are tested for zero.  A batch with any
-//      non-zero off-diagonal entry goes through solve_group (same results, generic path).
+//      non-zero off-diagonal entry goes through solve_group (generic path).
 //   2. The per-problem constants (lambda_max by power iteration, rho_0, tau_0, (P + (rho+mu) I)^-1) are computed
-//      four problems at a time on all 32 lanes; the two pow() calls of all 16 problems are ONE call per lane.
-//   3. The ADMM loop runs on four tile slots.  A slot whose problem stops stores x*, takes the next problem of
-//      the batch from the queue and restarts; the queue is ordered by the smallest diagonal entry (ascending):
-//      ill-conditioned problems are the slow ones, so they start first (longest-processing-time-first) and the
-//      batch's stragglers overlap the bulk instead of trailing it.
+//      four problems at a time on all 32 lanes; the two pow() calls of a warp's 16 problems are ONE call per lane.
+//   3. The ADMM loop runs on 4 tile slots per warp, all fed from ONE queue per CTA.  A slot whose problem stops
+//      stores x*, takes the next problem of the queue and restarts; the queue is ordered by the smallest diagonal
+//      entry (ascending): ill-conditioned problems are the slow ones, so they start first (longest-processing-time-
+//      first), the warps of a CTA finish together, and the batch's stragglers overlap the bulk instead of trailing it.
 // Per-problem arithmetic is the generic path's, operation for operation: results are bit-identical.
-constexpr int DIAG_SLOTS = 16;  // problems per batch (queue capacity per warp)
+constexpr int DIAG_SLOTS = 16;  // problems per warp and batch
 #ifndef DQ_DIAG_WARPS
-#define DQ_DIAG_WARPS 1
+#define DQ_DIAG_WARPS 4
 #endif
-constexpr int DIAG_WARPS = DQ_DIAG_WARPS;  // warps per CTA: one, so that a finished warp's slot frees at once (measured best)
+constexpr int DIAG_WARPS = DQ_DIAG_WARPS;          // warps per CTA, sharing one queue
+constexpr int DIAG_CAP = DIAG_SLOTS * DIAG_WARPS;  // problems per CTA batch
 
 template <int PROX>
 struct DiagRec {  // one problem's record in shared memory, in doubles
@@ -461,323 +462,341 @@ struct DiagRec {  // one problem's record in shared memory, in doubles
   static constexpr int X0 = 24;    // disk radius | l_min
   static constexpr int X1 = 32;    // l_max
   static constexpr int X2 = 40;    // sign(v)
-  static constexpr int RHO = 8 * NV, TAU = RHO + 1, IRHO = RHO + 2, LMAX = RHO + 3;  // tau_inc
-  static constexpr int TAUD = LMAX;  // tau_dec takes lambda_max's place once rho_0 is known
+  static constexpr int RHO = 8 * NV, TAU = RHO + 1, IRHO = RHO + 2, LMAX = RHO + 3;
+  static constexpr int TAUI = Q, TAUD = PINV;  // per-lane tau_inc / tau_dec of a running problem (see take())
   static constexpr int D = 8 * NV + 4;
-  // per warp: the records, then 16 uint32 keys + 16 int queue entries
-  static constexpr int per_warp_doubles =
-      (DIAG_SLOTS * D + 16 > FwdSmem<8>::per_warp_doubles) ? DIAG_SLOTS * D + 16 : FwdSmem<8>::per_warp_doubles;
-  static constexpr size_t bytes = (size_t)DIAG_WARPS * per_warp_doubles * sizeof(double);
+  static_assert(DIAG_SLOTS * D >= FwdSmem<8>::per_warp_doubles, "a warp's records double as the generic path's scratch");
+  // the records, then per problem a uint32 key and an int queue entry, then the queue head and the dense flag
+  static constexpr size_t bytes = (size_t)DIAG_CAP * D * sizeof(double) + DIAG_CAP * 8 + 16;
 };
 
 template <int PROX>
-__device__ __forceinline__ void diag8_batch(const FwdParams& p, const long long b0, const int nb, const int lane,
-                                            double* wsm) {
+__global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? 32 : 28) / DIAG_WARPS)
+    admm_fwd_diag8_kernel(const FwdParams p) {
   using R = DiagRec<PROX>;
   constexpr bool QCQP = (PROX == PROX_DISK);
   constexpr int T = 8;
-  double* recs = wsm;
-  unsigned* keys = reinterpret_cast<unsigned*>(wsm + DIAG_SLOTS * R::D);  // [16] order keys
-  int* order = reinterpret_cast<int*>(keys + 16);                         // [16] queue: position -> record
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* recs = reinterpret_cast<double*>(smem_raw);
+  unsigned* keys = reinterpret_cast<unsigned*>(recs + DIAG_CAP * R::D);  // [CAP] order keys
+  int* order = reinterpret_cast<int*>(keys + DIAG_CAP);                  // [CAP] queue: position -> record
+  int* ctl = order + DIAG_CAP;                                           // [0] queue head, [1] dense flag
+  const int lane = threadIdx.x & 31;
+  // the warp index through a shuffle: the compiler then knows it to be warp-uniform and does not guard every vote /
+  // shuffle below with a divergence check
+  const int warp = __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
   const int ti = lane & 7, tp = lane >> 3, tile_base = tp * 8;
   const double mu = p.mu_prox, eps = p.eps;
+  const long long c0 = (p.B * blockIdx.x) / gridDim.x, c1 = (p.B * (blockIdx.x + 1LL)) / gridDim.x;  // this CTA's chunk
 
-  // ---- 1. P: flat stream.  Lane l of load k holds row (l & 15) >> 1, columns 4 (l & 1) .. +3 of problem 2k + (l >> 4).
-  bool nz = false;
-  {
-    const int r = (lane & 15) >> 1;
-    const bool has_diag = (r >> 2) == (lane & 1);
-    const int d = r & 3;
-    const double* src = p.P + b0 * 64 + lane * 4;
+  const long long nchunk = c1 - c0;
+  const int nbat = (int)((nchunk + DIAG_CAP - 1) / DIAG_CAP);  // batches of equal size (never a tiny last one)
+  for (int ib = 0; ib < nbat; ib++) {
+    const long long b0 = c0 + (nchunk * ib) / nbat;
+    const int nb = (int)(c0 + (nchunk * (ib + 1)) / nbat - b0);  // problems in this batch (CTA-uniform), <= DIAG_CAP
+    const int w0 = warp * DIAG_SLOTS;                                 // this warp sets up records w0 .. w0 + nw - 1
+    const int nw = nb - w0 < 0 ? 0 : (nb - w0 < DIAG_SLOTS ? nb - w0 : DIAG_SLOTS);
+    if (threadIdx.x == 0) {
+      ctl[0] = DIAG_WARPS * 4;  // the first 4 * DIAG_WARPS queue positions go to the slots directly
+      ctl[1] = 0;
+    }
+    __syncthreads();
+
+    // ---- 1. P: flat stream.  Lane l of load k holds row (l & 15) >> 1, columns 4 (l & 1) .. +3 of problem 2k + (l >> 4).
+    {
+      bool nz = false;
+      const int r = (lane & 15) >> 1;
+      const bool has_diag = (r >> 2) == (lane & 1);
+      const int d = r & 3;
+      const double* src = p.P + (b0 + w0) * 64 + lane * 4;
 #pragma unroll
-    for (int k0 = 0; k0 < DIAG_SLOTS / 2; k0 += 4) {
-      if (2 * k0 < nb) {  // warp-uniform
-        double v[4][4];
+      for (int k0 = 0; k0 < DIAG_SLOTS / 2; k0 += 4) {
+        if (2 * k0 < nw) {  // warp-uniform
+          double v[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.0;
-          if (2 * (k0 + k) + (lane >> 4) < nb)
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                         : "=d"(v[k][0]), "=d"(v[k][1]), "=d"(v[k][2]), "=d"(v[k][3])
-                         : "l"(src + (k0 + k) * 128));
-        }
+          for (int k = 0; k < 4; k++) {
+            v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.0;
+            if (2 * (k0 + k) + (lane >> 4) < nw)
+              asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                           : "=d"(v[k][0]), "=d"(v[k][1]), "=d"(v[k][2]), "=d"(v[k][3])
+                           : "l"(src + (k0 + k) * 128));
+          }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int j = 2 * (k0 + k) + (lane >> 4);
-          const double dv = d == 0 ? v[k][0] : (d == 1 ? v[k][1] : (d == 2 ? v[k][2] : v[k][3]));
-          const int cnt = (v[k][0] != 0.0) + (v[k][1] != 0.0) + (v[k][2] != 0.0) + (v[k][3] != 0.0);
-          nz |= cnt > ((has_diag && dv != 0.0) ? 1 : 0);
-          if (has_diag && j < nb) recs[j * R::D + R::M + r] = dv;
+          for (int k = 0; k < 4; k++) {
+            const int j = 2 * (k0 + k) + (lane >> 4);
+            const double dv = d == 0 ? v[k][0] : (d == 1 ? v[k][1] : (d == 2 ? v[k][2] : v[k][3]));
+            const int cnt = (v[k][0] != 0.0) + (v[k][1] != 0.0) + (v[k][2] != 0.0) + (v[k][3] != 0.0);
+            nz |= cnt > ((has_diag && dv != 0.0) ? 1 : 0);
+            if (has_diag && j < nw) recs[(w0 + j) * R::D + R::M + r] = dv;
+          }
         }
       }
+      if (__any_sync(FULL_MASK, nz) && lane == 0) ctl[1] = 1;
     }
-  }
-  if (__any_sync(FULL_MASK, nz) || p.max_iter <= 0) {  // dense batch (or nothing to iterate): the generic path
+    __syncthreads();
+    if (ctl[1] != 0 || p.max_iter <= 0) {  // a dense problem in the batch (or nothing to iterate): the generic path,
+      __syncthreads();                     // groups of four handed to the warps as they become free
+      if (threadIdx.x == 0) ctl[0] = 0;
+      __syncthreads();
+      while (true) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(&ctl[0], 1);
+        g = __shfl_sync(FULL_MASK, g, 0);
+        if (4 * g >= nb) break;
+        solve_group<8, PROX>(p, b0 + 4 * g, b0 + nb, lane, recs + w0 * R::D);
+        __syncwarp();
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- 2a. four problems per pass: q (and the prox data) into the record, lambda_max, the order key
+    for (int k = 0; 4 * k < nw; k++) {
+      const int j = 4 * k + tp;
+      const bool valid = j < nw;
+      double* rec = recs + (w0 + j) * R::D;
+      const double pd = valid ? rec[R::M + ti] : 1.0;
+      if (valid) {
+        const long long e = (b0 + w0 + j) * 8 + ti;
+        rec[R::Q + ti] = __ldg(p.q + e);
+        if (QCQP) {  // mul_n = l_n o mu   pybindings.cpp:57
+          const long long c = (b0 + w0 + j) * 4 + (ti >> 1);
+          rec[R::X0 + ti] = __dmul_rn(__ldg(p.l_n + c), __ldg(p.mu + c));
+        }
+        if (R::BOX) {
+          rec[R::X0 + ti] = __ldg(p.lo + e);
+          rec[R::X1 + ti] = __ldg(p.hi + e);
+          if (PROX == PROX_SIGNED_BOX) {
+            const double v = __ldg(p.vsign + e);
+            rec[R::X2 + ti] = v > 0 ? 1.0 : (v < 0 ? -1.0 : 0.0);  // v.cwiseSign()  Solver.cpp:391
+          }
+        }
+      }
+      // power_iteration (Solver.cpp:46-59) exactly as in solve_group: P v = p_ii v_i
+      double w = valid ? 1.0 : 0.0;
+      const int K = QCQP ? 100 : 10;
+      for (int kk = 0; kk < K; kk++) {
+        w = __dmul_rn(pd, w);
+        if ((kk & 3) == 3 || kk == K - 1) w = __dmul_rn(w, tile_pow2_rescale<T>(w));
+      }
+      const double z = tile_sum<T>(__dmul_rn(w, w));
+      const double v = (z > 0) ? w / sqrt(z) : w;
+      const double Lmax = tile_sum<T>(__dmul_rn(v, __dmul_rn(pd, v)));
+      unsigned key = (unsigned)__double2hiint(pd) & 0x7fffffffu;  // smallest |p_ii| of the problem (high word)
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL_MASK, key, o));
+      if (valid && ti == 0) {
+        rec[R::LMAX] = Lmax;
+        keys[w0 + j] = key;
+      }
+    }
     __syncwarp();
-    for (int k = 0; 4 * k < nb; k++) {
-      solve_group<8, PROX>(p, b0 + 4 * k, b0 + nb, lane, wsm);
-      __syncwarp();
-    }
-    return;
-  }
-  __syncwarp();
-
-  // ---- 2a. four problems per pass: q (and the prox data) into the record, lambda_max, the order key
-  for (int k = 0; 4 * k < nb; k++) {
-    const int j = 4 * k + tp;
-    const bool valid = j < nb;
-    double* rec = recs + j * R::D;
-    const double pd = valid ? rec[R::M + ti] : 1.0;
-    if (valid) {
-      const long long e = (b0 + j) * 8 + ti;
-      rec[R::Q + ti] = __ldg(p.q + e);
-      if (QCQP) {  // mul_n = l_n o mu   pybindings.cpp:57
-        const long long c = (b0 + j) * 4 + (ti >> 1);
-        rec[R::X0 + ti] = __dmul_rn(__ldg(p.l_n + c), __ldg(p.mu + c));
+    // ---- 2b. rho_0 / tau_0 (Solver.cpp:72-73, :531-532) for the warp's 16 problems: lane l -> problem l >> 1, exponent by l & 1
+    if (nw > 0) {
+      const int j = lane >> 1;
+      const bool valid = j < nw;
+      double* rec = recs + (w0 + j) * R::D;
+      const double Lmax = valid ? rec[R::LMAX] : 1.0;
+      const double pw = pow(Lmax / mu, (lane & 1) ? .15 : .4);
+      const double pw4 = __shfl_sync(FULL_MASK, pw, lane & ~1);
+      const double tau = __shfl_sync(FULL_MASK, pw, lane | 1);
+      const double rho = __dmul_rn(sqrt(__dmul_rn(mu, Lmax)), pw4);
+      if (valid && !(lane & 1)) {
+        rec[R::RHO] = rho;
+        rec[R::TAU] = tau;
+        rec[R::IRHO] = 1.0 / rho;
       }
-      if (R::BOX) {
-        rec[R::X0 + ti] = __ldg(p.lo + e);
-        rec[R::X1 + ti] = __ldg(p.hi + e);
+    }
+    __syncwarp();
+    // ---- 2c. P += (rho + mu) I and its inverse (:75-77): LLT of a diagonal matrix, two substitutions against I
+    for (int k = 0; 4 * k < nw; k++) {
+      const int j = 4 * k + tp;
+      if (j < nw) {
+        double* rec = recs + (w0 + j) * R::D;
+        const double m = __dadd_rn(rec[R::M + ti], __dadd_rn(rec[R::RHO], mu));
+        const double a = 1.0 / sqrt(m);
+        rec[R::M + ti] = m;
+        rec[R::PINV + ti] = __dmul_rn(a, a);
+      }
+    }
+    __syncthreads();
+    // ---- 2d. queue order: ascending key, ties by index
+    for (int t = threadIdx.x; t < nb; t += DIAG_WARPS * 32) {
+      const unsigned mykey = keys[t];
+      int rank = 0;
+      for (int i = 0; i < nb; i++) {
+        const unsigned ki = keys[i];
+        rank += (ki < mykey) || (ki == mykey && i < t);
+      }
+      order[rank] = t;
+    }
+    __syncthreads();
+
+    // ---- 3. the ADMM loop (Solver.cpp:79-121 / :538-580) on this warp's four tile slots, refilled from the CTA's
+    // queue; see admm_loop for the decision and pipelining scheme, which is the same
+    const bool odd = lane & 1;
+    unsigned tmask = 0xffu << tile_base;
+    asm volatile("" : "+r"(tmask));  // keep it in a register (otherwise rematerialised from %tid in every trip)
+    // Per-lane state kept in registers: what every iteration reads.  What only a rho update touches (tau_inc, tau_dec,
+    // m_ii) stays in the problem's record.
+    double qi = 0.0, pinvd = 1.0, rho = 1.0, irho = 1.0;
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0;  // radius | l_min, l_max, sign(v)
+    int live = 0;
+    int rho_up = 0, cpt5 = 0, it = 0;
+    double* rec = recs;  // this tile's current record
+    int nlive = 0;       // warp-uniform: tile slots of this warp that hold a problem
+
+    struct Iter {
+      double l2, u, qprox, dl, du, l;
+    };
+    auto take = [&](int pos) {  // this tile starts the problem at queue position pos
+      rec = recs + order[pos] * R::D;
+      qi = rec[R::Q + ti];
+      pinvd = rec[R::PINV + ti];
+      rho = rec[R::RHO];
+      irho = rec[R::IRHO];
+      const double tau = rec[R::TAU];
+      rec[R::TAUI + ti] = tau;  // q_i and 1/m_ii now live in registers: their slots carry this lane's tau_inc / tau_dec
+      rec[R::TAUD + ti] = tau;
+      if (QCQP || R::BOX) x0 = rec[R::X0 + ti];
+      if (R::BOX) x1 = rec[R::X1 + ti];
+      if (PROX == PROX_SIGNED_BOX) x2 = rec[R::X2 + ti];
+      rho_up = 0; cpt5 = 0; it = 0;
+      live = 1;
+    };
+    auto step = [&](const Iter& s, Iter& o) {
+      const double rhs = __dsub_rn(__dsub_rn(__dmul_rn(rho, s.l2), s.u), s.qprox);  // :80
+      const double l = __dmul_rn(pinvd, rhs);
+      o.qprox = __dsub_rn(qi, __dmul_rn(mu, l));                                    // :81
+      const double relax = __dadd_rn(__dmul_rn(1.5, l), __dmul_rn(-0.5, s.l2));
+      const double z = __dadd_rn(relax, div_by(s.u, rho, irho));                    // :82
+      double l2n;
+      if (PROX == PROX_NONNEG) {
+        l2n = z < 0 ? 0.0 : z;
+      } else if (R::BOX) {
+        l2n = z < x0 ? x0 : z;
+        l2n = x1 < l2n ? x1 : l2n;
         if (PROX == PROX_SIGNED_BOX) {
-          const double v = __ldg(p.vsign + e);
-          rec[R::X2 + ti] = v > 0 ? 1.0 : (v < 0 ? -1.0 : 0.0);  // v.cwiseSign()  Solver.cpp:391
+          double w = __dmul_rn(x2, l2n);
+          w = 0 < w ? 0.0 : w;
+          l2n = __dmul_rn(x2, w);
+        }
+      } else {  // prox_circle :505-519
+        const double zo = __shfl_xor_sync(FULL_MASK, z, 1);
+        const double a0 = odd ? zo : z, a1 = odd ? z : zo;
+        const double nrm = sqrt(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)));
+        l2n = (nrm > x0) ? __dmul_rn(z, x0) / nrm : z;
+      }
+      o.du = __dsub_rn(relax, l2n);
+      o.u = __dadd_rn(s.u, __dmul_rn(rho, o.du));  // :83
+      o.dl = __dsub_rn(l2n, s.l2);                 // :84
+      o.l2 = l2n;
+      o.l = l;
+    };
+    // body(P, Q): Q = speculative next iteration; decide P; a finished tile stores x*, takes the next problem of the
+    // queue and computes its first iteration into Q; a tile whose rho changed recomputes Q.  For the prox that
+    // shuffles inside step (disks) the recomputation is done by the whole warp, tiles that did not change recompute
+    // the same bits.
+    auto body = [&](Iter& P, Iter& Q) {
+      step(P, Q);
+      ++it;
+      const double adl = fabs(P.dl), pdu = fabs(P.du);
+      bool stop = (__ballot_sync(FULL_MASK, __dmul_rn(rho, adl) < eps) & tmask) == tmask;  // :88 / :548
+      const double rd = __dmul_rn(rho, tile_absmax<T>(P.dl));
+      if (QCQP) {
+        if (__any_sync(FULL_MASK, stop && live)) {
+          const double thr = __dadd_rn(eps, __dmul_rn(1e-4, sqrt(tile_sum<T>(__dmul_rn(P.l, P.l)))));
+          const bool prim_ok = (__ballot_sync(FULL_MASK, pdu < thr) & tmask) == tmask;
+          stop = stop & prim_ok;
         }
       }
-    }
-    // power_iteration (Solver.cpp:46-59) exactly as in solve_group: P v = p_ii v_i
-    double w = valid ? 1.0 : 0.0;
-    const int K = QCQP ? 100 : 10;
-    for (int kk = 0; kk < K; kk++) {
-      w = __dmul_rn(pd, w);
-      if ((kk & 3) == 3 || kk == K - 1) w = __dmul_rn(w, tile_pow2_rescale<T>(w));
-    }
-    const double z = tile_sum<T>(__dmul_rn(w, w));
-    const double v = (z > 0) ? w / sqrt(z) : w;
-    const double Lmax = tile_sum<T>(__dmul_rn(v, __dmul_rn(pd, v)));
-    unsigned key = (unsigned)__double2hiint(pd) & 0x7fffffffu;  // smallest |p_ii| of the problem (high word)
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL_MASK, key, o));
-    if (valid && ti == 0) {
-      rec[R::LMAX] = Lmax;
-      keys[j] = key;
-    }
-  }
-  __syncwarp();
-  // ---- 2b. rho_0 / tau_0 (Solver.cpp:72-73, :531-532) for the whole batch: lane l -> problem l >> 1, exponent by l & 1
-  {
-    const int j = lane >> 1;
-    const bool valid = j < nb;
-    const double Lmax = valid ? recs[j * R::D + R::LMAX] : 1.0;
-    const double pw = pow(Lmax / mu, (lane & 1) ? .15 : .4);
-    const double pw4 = __shfl_sync(FULL_MASK, pw, lane & ~1);
-    const double tau = __shfl_sync(FULL_MASK, pw, lane | 1);
-    const double rho = __dmul_rn(sqrt(__dmul_rn(mu, Lmax)), pw4);
-    if (valid && !(lane & 1)) {
-      recs[j * R::D + R::RHO] = rho;
-      recs[j * R::D + R::TAU] = tau;
-      recs[j * R::D + R::IRHO] = 1.0 / rho;
-    }
-    __syncwarp();
-    if (valid && !(lane & 1)) recs[j * R::D + R::TAUD] = tau;  // after every lane has read lambda_max
-    // queue order: ascending key, ties by index (lanes 0..15 rank their own problem)
-    const int jj = lane & 15;
-    const unsigned mykey = jj < nb ? keys[jj] : 0xffffffffu;
-    int rank = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const unsigned ki = __shfl_sync(FULL_MASK, mykey, i);
-      rank += (ki < mykey) || (ki == mykey && i < jj);
-    }
-    __syncwarp();
-    if (lane < 16) order[rank] = jj;
-  }
-  __syncwarp();
-  // ---- 2c. P += (rho + mu) I and its inverse (:75-77): LLT of a diagonal matrix, two substitutions against I
-  for (int k = 0; 4 * k < nb; k++) {
-    const int j = 4 * k + tp;
-    if (j < nb) {
-      double* rec = recs + j * R::D;
-      const double m = __dadd_rn(rec[R::M + ti], __dadd_rn(rec[R::RHO], mu));
-      const double a = 1.0 / sqrt(m);
-      rec[R::M + ti] = m;
-      rec[R::PINV + ti] = __dmul_rn(a, a);
-    }
-  }
-  __syncwarp();
-
-  // ---- 3. the ADMM loop (Solver.cpp:79-121 / :538-580) on four refilled tile slots; see admm_loop for the
-  // decision and pipelining scheme, which is the same
-  const bool odd = lane & 1;
-  unsigned tmask = 0xffu << tile_base;
-  asm volatile("" : "+r"(tmask));  // keep it in a register (otherwise rematerialised from %tid in every trip)
-  // Per-lane state kept in registers: what every iteration reads.  What only a rho update touches (tau_inc, tau_dec,
-  // m_ii) stays in the problem's record.
-  double qi = 0.0, pinvd = 1.0, rho = 1.0, irho = 1.0;
-  double x0 = 0.0, x1 = 0.0, x2 = 0.0;  // radius | l_min, l_max, sign(v)
-  int live = 0;
-  int rho_up = 0, cpt5 = 0, it = 0;
-  double* rec = recs;      // this tile's current record
-  int head = 4, done = 0;  // warp-uniform: next queue position to hand out, problems finished
-
-  struct Iter {
-    double l2, u, qprox, dl, du, l;
-  };
-  auto take = [&](int pos) {  // this tile starts the problem at queue position pos
-    rec = recs + order[pos] * R::D;
-    qi = rec[R::Q + ti];
-    pinvd = rec[R::PINV + ti];
-    rho = rec[R::RHO];
-    irho = rec[R::IRHO];
-    if (QCQP || R::BOX) x0 = rec[R::X0 + ti];
-    if (R::BOX) x1 = rec[R::X1 + ti];
-    if (PROX == PROX_SIGNED_BOX) x2 = rec[R::X2 + ti];
-    rho_up = 0; cpt5 = 0; it = 0;
-    live = 1;
-  };
-  auto step = [&](const Iter& s, Iter& o) {
-    const double rhs = __dsub_rn(__dsub_rn(__dmul_rn(rho, s.l2), s.u), s.qprox);  // :80
-    const double l = __dmul_rn(pinvd, rhs);
-    o.qprox = __dsub_rn(qi, __dmul_rn(mu, l));                                    // :81
-    const double relax = __dadd_rn(__dmul_rn(1.5, l), __dmul_rn(-0.5, s.l2));
-    const double z = __dadd_rn(relax, div_by(s.u, rho, irho));                    // :82
-    double l2n;
-    if (PROX == PROX_NONNEG) {
-      l2n = z < 0 ? 0.0 : z;
-    } else if (R::BOX) {
-      l2n = z < x0 ? x0 : z;
-      l2n = x1 < l2n ? x1 : l2n;
-      if (PROX == PROX_SIGNED_BOX) {
-        double w = __dmul_rn(x2, l2n);
-        w = 0 < w ? 0.0 : w;
-        l2n = __dmul_rn(x2, w);
-      }
-    } else {  // prox_circle :505-519
-      const double zo = __shfl_xor_sync(FULL_MASK, z, 1);
-      const double a0 = odd ? zo : z, a1 = odd ? z : zo;
-      const double nrm = sqrt(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)));
-      l2n = (nrm > x0) ? __dmul_rn(z, x0) / nrm : z;
-    }
-    o.du = __dsub_rn(relax, l2n);
-    o.u = __dadd_rn(s.u, __dmul_rn(rho, o.du));  // :83
-    o.dl = __dsub_rn(l2n, s.l2);                 // :84
-    o.l2 = l2n;
-    o.l = l;
-  };
-  // body(P, Q): Q = speculative next iteration; decide P; a finished tile stores x*, takes the next problem of the
-  // queue and computes its first iteration into Q; a tile whose rho changed recomputes Q.  For the prox that
-  // shuffles inside step (disks) the recomputation is done by the whole warp, tiles that did not change recompute
-  // the same bits.
-  auto body = [&](Iter& P, Iter& Q) {
-    step(P, Q);
-    ++it;
-    const double adl = fabs(P.dl), pdu = fabs(P.du);
-    bool stop = (__ballot_sync(FULL_MASK, __dmul_rn(rho, adl) < eps) & tmask) == tmask;  // :88 / :548
-    const double rd = __dmul_rn(rho, tile_absmax<T>(P.dl));
-    if (QCQP) {
-      if (__any_sync(FULL_MASK, stop && live)) {
-        const double thr = __dadd_rn(eps, __dmul_rn(1e-4, sqrt(tile_sum<T>(__dmul_rn(P.l, P.l)))));
-        const bool prim_ok = (__ballot_sync(FULL_MASK, pdu < thr) & tmask) == tmask;
-        stop = stop & prim_ok;
-      }
-    }
-    const bool inc = (__ballot_sync(FULL_MASK, pdu > __dmul_rn(10., rd)) & tmask) != 0u;     // :92 / :552
-    const bool dec = (__ballot_sync(FULL_MASK, rd > __dmul_rn(10., pdu)) & tmask) == tmask;  // :106 / :566
-    const bool fin = (live != 0) & (stop | (it >= p.max_iter));
-    const bool cnt = (live != 0) & !fin & (p.adaptive != 0) & (inc | dec);
-    bool redo = false;
-    if (cnt) {
-      if (cpt5 == 0) {  // adaptive rho :91-120 / :551-579; every lane of the tile writes the same tau values
-        double tau_inc = rec[R::TAU], tau_dec = rec[R::TAUD], mdiag = rec[R::M + ti];
-        if (inc) {
-          if (rho_up == -1) {
-            tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));
-            if (!QCQP) tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));
-          }
-          mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(tau_inc, 1)));
-          rho = __dmul_rn(rho, tau_inc);
-          rho_up = 1;
-        } else {
-          if (rho_up == 1) {
-            if (!QCQP) tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));
-            tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));
-          }
-          const double itau = 1. / tau_dec;
-          mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(itau, 1)));
-          rho = div_by(rho, tau_dec, itau);
-          rho_up = -1;
-        }
-        rec[R::TAU] = tau_inc;
-        rec[R::TAUD] = tau_dec;
-        rec[R::M + ti] = mdiag;
-        irho = 1.0 / rho;
-        const double a = 1.0 / sqrt(mdiag);
-        pinvd = __dmul_rn(a, a);
-        if (QCQP) redo = true;
-        else step(P, Q);
-      }
-      cpt5 = (cpt5 == 4) ? 0 : cpt5 + 1;
-    }
-    const unsigned fm = __ballot_sync(FULL_MASK, fin);
-    if (fm) {  // warp-uniform: at least one tile finished its problem on this iteration
-      const unsigned lead = fm & 0x01010101u;
-      if (fin) {
-        const long long prob = b0 + (int)(rec - recs) / R::D;
-        p.x[prob * 8 + ti] = P.l2;  // return l_2  :122 / :581
-        if (ti == 0 && p.iters) p.iters[prob] = it;
-        const int pos = head + __popc(lead & ((1u << tile_base) - 1u));
-        if (pos < nb) {
-          take(pos);
-          if (QCQP) {
-            P.l2 = 0.0; P.u = 0.0; P.qprox = qi;  // l_2 = u = 0, q_prox = q   :67-74
-            redo = true;
+      const bool inc = (__ballot_sync(FULL_MASK, pdu > __dmul_rn(10., rd)) & tmask) != 0u;     // :92 / :552
+      const bool dec = (__ballot_sync(FULL_MASK, rd > __dmul_rn(10., pdu)) & tmask) == tmask;  // :106 / :566
+      const bool fin = (live != 0) & (stop | (it >= p.max_iter));
+      const bool cnt = (live != 0) & !fin & (p.adaptive != 0) & (inc | dec);
+      bool redo = false;
+      if (cnt) {
+        if (cpt5 == 0) {  // adaptive rho :91-120 / :551-579; each lane keeps its own copy of the tile's taus
+          double tau_inc = rec[R::TAUI + ti], tau_dec = rec[R::TAUD + ti], mdiag = rec[R::M + ti];
+          if (inc) {
+            if (rho_up == -1) {
+              tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));
+              if (!QCQP) tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));
+            }
+            mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(tau_inc, 1)));
+            rho = __dmul_rn(rho, tau_inc);
+            rho_up = 1;
           } else {
-            Iter S;
-            S.l2 = 0.0; S.u = 0.0; S.qprox = qi;
-            step(S, Q);
+            if (rho_up == 1) {
+              if (!QCQP) tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));
+              tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));
+            }
+            const double itau = 1. / tau_dec;
+            mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(itau, 1)));
+            rho = div_by(rho, tau_dec, itau);
+            rho_up = -1;
           }
-        } else {
-          live = 0;
+          rec[R::TAUI + ti] = tau_inc;
+          rec[R::TAUD + ti] = tau_dec;
+          rec[R::M + ti] = mdiag;
+          irho = 1.0 / rho;
+          const double a = 1.0 / sqrt(mdiag);
+          pinvd = __dmul_rn(a, a);
+          if (QCQP) redo = true;
+          else step(P, Q);
+        }
+        cpt5 = (cpt5 == 4) ? 0 : cpt5 + 1;
+      }
+      const unsigned fm = __ballot_sync(FULL_MASK, fin);
+      if (fm) {  // warp-uniform: at least one tile of this warp finished its problem on this iteration
+        const unsigned lead = fm & 0x01010101u;
+        const int nfin = __popc(lead);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&ctl[0], nfin);  // nfin consecutive queue positions for this warp
+        base = __shfl_sync(FULL_MASK, base, 0);
+        int taken = nb - base;  // how many of them exist
+        taken = taken < 0 ? 0 : (taken > nfin ? nfin : taken);
+        nlive += taken - nfin;
+        if (fin) {
+          const long long prob = b0 + (int)(rec - recs) / R::D;
+          p.x[prob * 8 + ti] = P.l2;  // return l_2  :122 / :581
+          if (ti == 0 && p.iters) p.iters[prob] = it;
+          const int pos = base + __popc(lead & ((1u << tile_base) - 1u));
+          if (pos < nb) {
+            take(pos);
+            if (QCQP) {
+              P.l2 = 0.0; P.u = 0.0; P.qprox = qi;  // l_2 = u = 0, q_prox = q   :67-74
+              redo = true;
+            } else {
+              Iter S;
+              S.l2 = 0.0; S.u = 0.0; S.qprox = qi;
+              step(S, Q);
+            }
+          } else {
+            live = 0;
+          }
         }
       }
-      const int nfin = __popc(lead);
-      head += nfin;
-      done += nfin;
-    }
-    if (QCQP) {
-      if (__any_sync(FULL_MASK, redo)) step(P, Q);
-    }
-  };
+      if (QCQP) {
+        if (__any_sync(FULL_MASK, redo)) step(P, Q);
+      }
+    };
 
-  Iter A, B;
-  if (tp < nb) take(tp);
-  A.l2 = 0.0; A.u = 0.0; A.qprox = qi; A.dl = A.du = A.l = 0.0;
-  step(A, B);  // iteration 1, undecided
-  while (true) {  // ping-pong between the two register sets; done / nb are warp-uniform (uniform registers)
-    body(B, A);
-    if (done >= nb) break;
-    body(A, B);
-    if (done >= nb) break;
-  }
-}
-
-// Resident CTAs per SM the register budget is sized for: 8 x 128 threads x 64 registers for the QP (no spill inside
-// the loop); the other prox variants carry their bounds / radii in registers too and get 72 registers (7 CTAs).
-template <int PROX>
-__global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? 32 : 28) / DIAG_WARPS)
-    admm_fwd_diag8_kernel(const FwdParams p, const int n_warps) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  // the warp index through a shuffle: the compiler then knows it (and the loop bounds below) to be warp-uniform and
-  // does not guard every vote / shuffle of the loop with a divergence check
-  const long long w = (long long)blockIdx.x * DIAG_WARPS + __shfl_sync(FULL_MASK, warp, 0);
-  if (w >= n_warps) return;
-  double* wsm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * DiagRec<PROX>::per_warp_doubles;
-  const long long c0 = (p.B * w) / n_warps, c1 = (p.B * (w + 1)) / n_warps;  // this warp's contiguous chunk
-  for (long long b0 = c0; b0 < c1; b0 += DIAG_SLOTS) {
-    const long long left = c1 - b0;
-    diag8_batch<PROX>(p, b0, left < DIAG_SLOTS ? (int)left : DIAG_SLOTS, lane, wsm);
-    __syncwarp();
+    Iter A, B;
+    {
+      const int pos = warp * 4 + tp;
+      if (pos < nb) take(pos);
+      const int mine = nb - warp * 4;
+      nlive = mine < 0 ? 0 : (mine > 4 ? 4 : mine);
+    }
+    A.l2 = 0.0; A.u = 0.0; A.qprox = qi; A.dl = A.du = A.l = 0.0;
+    step(A, B);  // iteration 1, undecided
+    while (nlive > 0) {  // ping-pong between the two register sets; nlive is warp-uniform
+      body(B, A);
+      if (nlive <= 0) break;
+      body(A, B);
+    }
+    __syncthreads();  // the records are rewritten by the next batch
   }
 }
 
@@ -800,7 +819,7 @@ static cudaError_t launch_fwd_p(const FwdParams& p, int T, cudaStream_t stream) 
 }
 
 // ---- diagonal fast path launch: a persistent grid (every resident warp slot of the device), chunks balanced over it
-static int g_fwd_path = 0;  // 0 = automatic, 1 = generic kernel only (parity tests compare the two paths)
+static int g_fwd_path = 0;  // 0 = automatic, 1 = generic kernel only, 2 = persistent kernel wherever it applies (tests)
 int set_fwd_path(int path) {
   const int old = g_fwd_path;
   g_fwd_path = path;
@@ -809,36 +828,38 @@ int set_fwd_path(int path) {
 
 template <int PROX>
 static cudaError_t launch_diag8(const FwdParams& p, cudaStream_t stream) {
-  static int resident_warps[64] = {0};  // per device; a benign race writes the same value
+  static int resident_ctas[64] = {0};  // per device; a benign race writes the same value
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (resident_warps[dev] == 0) {
+  if (resident_ctas[dev] == 0) {
     int sms = 0, ctas = 0;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-#ifndef DQ_DIAG_NO_CARVEOUT
     cudaFuncSetAttribute(admm_fwd_diag8_kernel<PROX>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-#endif
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, admm_fwd_diag8_kernel<PROX>, DIAG_WARPS * 32,
                                                       DiagRec<PROX>::bytes);
     if (e != cudaSuccess) return e;
     if (sms < 1 || ctas < 1) return cudaErrorLaunchOutOfResources;
-    resident_warps[dev] = sms * ctas * DIAG_WARPS;
+    resident_ctas[dev] = sms * ctas;
   }
-  const long long by4 = (p.B + 3) / 4;  // a warp with fewer than four problems would idle tile slots
-  const int n_warps = (int)(by4 < resident_warps[dev] ? by4 : resident_warps[dev]);
-  const int grid = (n_warps + DIAG_WARPS - 1) / DIAG_WARPS;
-  admm_fwd_diag8_kernel<PROX><<<grid, DIAG_WARPS * 32, DiagRec<PROX>::bytes, stream>>>(p, n_warps);
+  // every resident CTA slot of the device gets a chunk; a CTA with fewer than four problems per warp would idle slots
+  const long long want = (p.B + 4 * DIAG_WARPS - 1) / (4 * DIAG_WARPS);
+  const int grid = (int)(want < resident_ctas[dev] ? want : resident_ctas[dev]);
+  admm_fwd_diag8_kernel<PROX><<<grid, DIAG_WARPS * 32, DiagRec<PROX>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
 // prox: 0 = x >= 0 (QP), 1 = per-contact disks (QCQP), 2 = box, 3 = box + sign constraint
 cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t stream) {
-  if (g_fwd_path == 0 && p.N == 8 && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0) {
-    switch (prox) {  // N == 8: persistent warps, diagonal batches on refilled tile slots, dense batches via solve_group
+  // N == 8, QP / Box prox: persistent CTAs, diagonal batches on refilled tile slots, dense batches via solve_group.
+  // The disk prox (QCQP) stays on the generic kernel: its iteration counts are too even for the refill to pay
+  // (measured: 116 us vs 98 us per 65536 diagonal problems).  g_fwd_path == 2 forces the persistent kernel for it too.
+  if (g_fwd_path != 1 && p.N == 8 && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0 &&
+      (prox != PROX_DISK || g_fwd_path == 2)) {
+    switch (prox) {
       case PROX_NONNEG: return launch_diag8<PROX_NONNEG>(p, stream);
       case PROX_DISK: return launch_diag8<PROX_DISK>(p, stream);
       case PROX_BOX: return launch_diag8<PROX_BOX>(p, stream);

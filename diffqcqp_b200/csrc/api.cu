@@ -103,8 +103,10 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
 // the stages (slot filled -> solved -> read back -> free).  Streams, events and device buffers are created
 // once per device and kept (grow-only), so a call costs no cudaMalloc / stream creation after the first.
 // Full PCIe rate needs page-locked host buffers (cudaHostAlloc / torch pin_memory); pageable memory works
-// but is staged by the driver.  Measured: 84 MB per B=65536 N=8 step in 1.24 ms; this box's PCIe does
-// 0.97 ms for the same bytes as two bare concurrent copies (scripts/micro/pcie.py).
+// but is staged by the driver.  Measured: 84 MB per B=65536 N=8 step in 1.24-1.30 ms; this box's PCIe does
+// 0.97 ms for the same bytes as two bare concurrent copies (scripts/micro/pcie.py).  Tried and measured no better
+// (1.31-1.42 ms): tapered chunk sizes (small first / last chunk), per-chunk copies of the vectors on the P stream,
+// and the first chunk's vector slices ahead of the rest; more than 6 chunks is slower (1.33 ms at 8, 1.44 at 16).
 struct HostJob {
   bool qcqp;
   const double *P, *q, *l_n, *mu, *grad_x;
@@ -350,7 +352,7 @@ int dq_max_n(void) { return DQ_MAX_N; }
 int dq_last_cuda_error(void) { return g_last_cuda_error; }
 int64_t dq_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 void dq_host_release(void) { host_release_all(); }
-int dq_set_forward_path(int path) { return dq::set_fwd_path(path == 1 ? 1 : 0); }
+int dq_set_forward_path(int path) { return dq::set_fwd_path(path == 1 || path == 2 ? path : 0); }
 
 const char* dq_error_string(int code) {
   switch (code) {

@@ -139,9 +139,10 @@ void dq_host_release(void);
 int64_t dq_launch_count(void);
 
 /*
- * Forward kernel selection (process-wide; for tests and A/B timing).  0 = automatic: N == 8 with a 32-byte aligned
- * P runs the persistent-warp kernel (diagonal batches on refilled tile slots), everything else the generic kernel.
- * 1 = generic kernel only.  Both produce bit-identical results.  Returns the previous setting.
+ * Forward kernel selection (process-wide; for tests and A/B timing).  0 = automatic: the QP / Box QP with N == 8 and a
+ * 32-byte aligned P runs the persistent-CTA kernel (diagonal batches on refilled tile slots), everything else the
+ * generic kernel.  1 = generic kernel only.  2 = persistent kernel wherever it applies (also the QCQP at N == 8).
+ * The kernels produce bit-identical results on batches that are all diagonal or all dense.  Returns the previous setting.
  */
 int dq_set_forward_path(int path);
 

@@ -19,6 +19,22 @@ for N, B in ((8, 37), (5, 9), (16, 10), (24, 5), (32, 3)):
     run(f"signed box N={N}", lambda: dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200, v=v))
 P, q, g = wl.qp_diag(70, 8, seed=1)
 run("qp diag N=8", lambda: dq.qp_backward(P.cuda(), q.cuda(), dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 500), g.cuda()))
+# the persistent-CTA forward (N == 8): shared queue with refills (several problems per tile slot), every prox, a
+# batch that mixes a dense problem in (generic group routine inside the persistent kernel)
+from diffqcqp_b200 import _lib
+L = _lib.load()
+P, q, g = wl.qp_diag(300, 8, seed=2)
+Pd, qd = P.cuda(), q.cuda()
+lo, hi, v = -torch.rand_like(qd), torch.rand_like(qd), torch.randn_like(qd)
+run("persistent qp diag N=8 B=300", lambda: dq.qp_forward(Pd, qd, 1e-7, 500))
+run("persistent box diag N=8", lambda: dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200))
+run("persistent signed box diag N=8", lambda: dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200, v=v))
+Pm = Pd.clone(); Pm[17] = wl.qp_dense(1, 8, seed=3)[0][0].cuda()
+run("persistent qp mixed N=8", lambda: dq.qp_forward(Pm, qd, 1e-7, 200))
+Pq, qq, l_n, mu, _ = wl.qcqp_diag(150, 8, seed=4)
+L.dq_set_forward_path(2)
+run("persistent qcqp diag N=8", lambda: dq.qcqp_forward(Pq.cuda(), qq.cuda(), l_n.cuda(), mu.cuda(), 1e-7, 200))
+L.dq_set_forward_path(0)
 for N, B, diag in ((8, 21, False), (8, 21, True), (6, 7, False), (16, 9, False), (24, 4, False), (32, 3, False), (32, 3, True)):
     P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=N, diag=diag)
     a = [t.cuda() for t in (P, q, l_n, mu)]

@@ -711,7 +711,7 @@ def test_forward_paths_bit_identical_variants(dq, wl, cuda_lib):
         try:
             cuda_lib.dq_set_forward_path(1)
             a = fn()
-            cuda_lib.dq_set_forward_path(0)
+            cuda_lib.dq_set_forward_path(2)
             b = fn()
         finally:
             cuda_lib.dq_set_forward_path(0)
