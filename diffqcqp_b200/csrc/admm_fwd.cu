@@ -125,6 +125,7 @@ enum : int { PROX_NONNEG = 0, PROX_DISK = 1, PROX_BOX = 2, PROX_SIGNED_BOX = 3 }
 
 struct FwdTile {  // what one lane knows about its problem when the ADMM loop starts
   double qi, pdiag, radius, rho, tau;
+  double ws, u0;      // start of l_2 and of the multiplier u (0 unless the warm-start extension is on)
   double lo, hi, vs;  // box bounds and sign(v) of this element (Box / SignedBox QP)
   const double* Prow;
   bool valid, vprob, vec32;
@@ -277,7 +278,10 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
   };
 
   Iter A, B;
-  A.l2 = 0.0; A.u = 0.0; A.qprox = t.qi; A.dl = A.du = A.l = 0.0;  // l_2 = u = 0, q_prox = q   :67-74
+  // l_2 = u = 0, q_prox = q   :67-74.  Warm-start extension (off by default, not reference behaviour): l_2 = l_2_pred =
+  // warm_start, u = -(P warm_start + q) (the multiplier of l = l_2 if warm_start were a KKT point) and the proximal term
+  // centred there, q_prox = q - mu warm_start.  With the extension off ws = u0 = 0 and these are the reference's bits.
+  A.l2 = t.ws; A.u = t.u0; A.qprox = __dsub_rn(t.qi, __dmul_rn(mu, t.ws)); A.dl = A.du = A.l = 0.0;
   if constexpr (DENSE) {
     while (__any_sync(FULL_MASK, live)) {  // warp ballot: leave when every problem of the group has finished
       if (__any_sync(FULL_MASK, refac)) refactor();
@@ -339,6 +343,7 @@ __device__ __forceinline__ void solve_group(const FwdParams& p, long long first,
   double prow[T];
   load_row<T>(prow, t.Prow, N, t.valid, t.vec32);
   t.qi = t.valid ? __ldg(p.q + prob * N + ti) : 0.0;
+  t.ws = (p.warm != nullptr && t.valid) ? __ldg(p.warm + prob * N + ti) : 0.0;
   t.radius = 0.0;
   if (QCQP) {
     const int nc = N >> 1;
@@ -378,6 +383,12 @@ __device__ __forceinline__ void solve_group(const FwdParams& p, long long first,
     cur ^= 1;
     return row_dot<T>(prow, vb + tile_base, N);
   };
+
+  t.u0 = 0.0;
+  if (p.warm != nullptr) {  // warp-uniform
+    const double pw = matvec(t.valid ? t.ws : 0.0);
+    if (t.valid) t.u0 = -__dadd_rn(pw, t.qi);
+  }
 
   // ---- power_iteration (Solver.cpp:46-59): fixed count, 10 for the QP (:71), 100 for the QCQP (:530).
   // The reference divides by |Pv| after every product; the direction of v does not depend on those
@@ -857,8 +868,8 @@ cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t st
   // N == 8, QP / Box prox: persistent CTAs, diagonal batches on refilled tile slots, dense batches via solve_group.
   // The disk prox (QCQP) stays on the generic kernel: its iteration counts are too even for the refill to pay
   // (measured: 116 us vs 98 us per 65536 diagonal problems).  g_fwd_path == 2 forces the persistent kernel for it too.
-  if (g_fwd_path != 1 && p.N == 8 && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0 &&
-      (prox != PROX_DISK || g_fwd_path == 2)) {
+  if (g_fwd_path != 1 && p.N == 8 && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0 && p.warm == nullptr &&
+      (prox != PROX_DISK || g_fwd_path == 2)) {  // (warm-started batches: generic kernel; their iteration counts are short and even)
     switch (prox) {
       case PROX_NONNEG: return launch_diag8<PROX_NONNEG>(p, stream);
       case PROX_DISK: return launch_diag8<PROX_DISK>(p, stream);

@@ -39,9 +39,12 @@ int check_common(const void* P, const void* q, const void* x, long long B, int N
 int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n, const double* mu, double* x,
                  int32_t* iters, long long B, int N, double eps, double mu_prox, int max_iter, int adaptive,
                  cudaStream_t stream, const double* l_min = nullptr, const double* l_max = nullptr,
-                 const double* v = nullptr) {
+                 const double* v = nullptr, const double* warm_start = nullptr) {
   int rc = check_common(P, q, x, B, N);
   if (rc != DQ_OK) return rc;
+  const bool warm = (adaptive & DQ_FLAG_WARM_START) != 0;  // extension: off unless the caller sets the flag bit
+  if (warm && B > 0 && !warm_start) return DQ_ERR_BAD_ARG;
+  if (warm && !aligned8(warm_start)) return DQ_ERR_ALIGN;
   if (qcqp) {
     if (N % 2 != 0) return DQ_ERR_BAD_ARG;
     if (B > 0 && (!l_n || !mu)) return DQ_ERR_BAD_ARG;
@@ -53,7 +56,9 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
   dq::FwdParams p;
   p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.iters = iters;
   p.lo = l_min; p.hi = l_max; p.vsign = v;
-  p.B = B; p.N = N; p.eps = eps; p.mu_prox = mu_prox; p.max_iter = max_iter; p.adaptive = adaptive ? 1 : 0;
+  p.warm = warm ? warm_start : nullptr;
+  p.B = B; p.N = N; p.eps = eps; p.mu_prox = mu_prox; p.max_iter = max_iter;
+  p.adaptive = (adaptive & DQ_FLAG_ADAPTIVE_RHO) ? 1 : 0;
   p.n_groups = (B + G - 1) / G;
   const int prox = qcqp ? 1 : (l_min ? (v ? 3 : 2) : 0);
   cudaError_t e = dq::launch_admm_fwd(p, prox, T, stream);
@@ -368,9 +373,9 @@ const char* dq_error_string(int code) {
 int dq_qp_forward(const double* P, const double* q, const double* warm_start, double* x, int32_t* iters,
                   int64_t B, int32_t N, double eps, double mu_prox, int32_t max_iter, int32_t adaptative_rho,
                   void* stream) {
-  (void)warm_start;  // dead in the reference: Solver.cpp:70 -> :80
+  // warm_start is dead in the reference (Solver.cpp:70 -> :80): read only when DQ_FLAG_WARM_START is set
   return forward_impl(false, P, q, nullptr, nullptr, x, iters, B, N, eps, mu_prox, max_iter, adaptative_rho,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, nullptr, nullptr, nullptr, warm_start);
 }
 
 int dq_qp_backward(const double* P, const double* q, const double* x, const double* grad_x, double* grad_P,
@@ -382,9 +387,9 @@ int dq_qp_backward(const double* P, const double* q, const double* x, const doub
 int dq_qcqp_forward(const double* P, const double* q, const double* l_n, const double* mu,
                     const double* warm_start, double* x, int32_t* iters, int64_t B, int32_t N, double eps,
                     double mu_prox, int32_t max_iter, int32_t adaptative_rho, void* stream) {
-  (void)warm_start;  // dead in the reference: Solver.cpp:529 -> :539
+  // warm_start is dead in the reference (Solver.cpp:529 -> :539): read only when DQ_FLAG_WARM_START is set
   return forward_impl(true, P, q, l_n, mu, x, iters, B, N, eps, mu_prox, max_iter, adaptative_rho,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, nullptr, nullptr, nullptr, warm_start);
 }
 
 int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const double* mu, const double* x,
@@ -397,11 +402,11 @@ int dq_qcqp_backward(const double* P, const double* q, const double* l_n, const 
 int dq_boxqp_forward(const double* P, const double* q, const double* l_min, const double* l_max, const double* v,
                      const double* warm_start, double* x, int32_t* iters, int64_t B, int32_t N, double eps,
                      double mu_prox, int32_t max_iter, int32_t adaptative_rho, void* stream) {
-  (void)warm_start;  // dead in the reference: Solver.cpp:207 -> :217, :383 -> :394
+  // warm_start is dead in the reference (Solver.cpp:207 -> :217, :383 -> :394): read only with DQ_FLAG_WARM_START
   if (B > 0 && (!l_min || !l_max)) return DQ_ERR_BAD_ARG;
   if (!aligned8(l_min) || !aligned8(l_max) || !aligned8(v)) return DQ_ERR_ALIGN;
   return forward_impl(false, P, q, nullptr, nullptr, x, iters, B, N, eps, mu_prox, max_iter, adaptative_rho,
-                      (cudaStream_t)stream, l_min, l_max, v);
+                      (cudaStream_t)stream, l_min, l_max, v, warm_start);
 }
 
 int dq_boxqp_backward(const double* P, const double* q, const double* l_min, const double* l_max, const double* x,

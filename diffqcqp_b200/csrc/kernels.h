@@ -14,6 +14,7 @@ struct FwdParams {
   const double* lo;     // Box / SignedBox QP only: l_min
   const double* hi;     // Box / SignedBox QP only: l_max
   const double* vsign;  // SignedBox QP only: v
+  const double* warm;   // NULL (the reference's behaviour: warm_start is dead) or the (B,N) start of l_2 (DQ_FLAG_WARM_START)
   double* x;
   int32_t* iters;  // nullable
   long long B;

@@ -14,7 +14,10 @@ Devices.  The reference is CPU-only (``.numpy()`` at qcqp.py:30).  Here:
 There is no CPU compute path: without the CUDA extension or a CUDA device this raises.
 
 Notes carried over from the reference's behaviour:
-  * ``warm_start`` is accepted and ignored, as in the reference (Solver.cpp:70 -> :80 overwrites it).
+  * ``warm_start`` is accepted and ignored, as in the reference (Solver.cpp:70 -> :80 overwrites it) -- unless the
+    caller opts into the extension with ``use_warm_start(True)``: the ADMM iteration then starts
+    at ``warm_start`` instead of zero (fewer iterations when it is close to the solution, e.g. the previous time step
+    of a simulator; results then differ from the reference's within its own stopping tolerance).
   * backward uses the binding's default ``epsilon=1e-10`` regardless of the forward ``eps``
     (qcqp.py:47,168; pybindings.cpp:80,82).
   * ``adaptative_rho`` is fixed to True (qcqp.py:27,148).
@@ -27,7 +30,41 @@ from torch.autograd import Function
 from . import _lib
 
 __all__ = ["QPFn2", "QCQPFn2", "BoxQPFn2", "SignedBoxQPFn2", "qp_forward", "qp_backward", "qcqp_forward",
-           "qcqp_backward", "boxqp_forward", "boxqp_backward"]
+           "qcqp_backward", "boxqp_forward", "boxqp_backward", "use_warm_start"]
+
+FLAG_ADAPTIVE_RHO, FLAG_WARM_START = 1, 2  # include/diffqcqp_b200.h: DQ_FLAG_*
+_warm_start_enabled = False
+
+
+class use_warm_start:
+    """Opt into the warm-start extension for the layers (``QPFn2`` ... read ``warm_start`` instead of ignoring it).
+    ``use_warm_start(True)`` switches it on process-wide; as a context manager it restores the previous setting."""
+
+    def __init__(self, enabled: bool = True):
+        global _warm_start_enabled
+        self.prev = _warm_start_enabled
+        _warm_start_enabled = bool(enabled)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        global _warm_start_enabled
+        _warm_start_enabled = self.prev
+        return False
+
+
+def _flags(adaptative_rho, warm_start):
+    return (FLAG_ADAPTIVE_RHO if adaptative_rho else 0) | (FLAG_WARM_START if warm_start is not None else 0)
+
+
+def _layer_warm(warm_start, dev, like):
+    """The layers' warm_start argument: None (ignored, the reference's behaviour) unless use_warm_start is on."""
+    if not _warm_start_enabled or warm_start is None:
+        return None
+    if tuple(warm_start.shape) != tuple(like.shape):
+        raise ValueError(f"warm_start must have shape {tuple(like.shape)}, got {tuple(warm_start.shape)}")
+    return _as_dev(warm_start, dev, "warm_start")
 
 
 def _ptr(t):
@@ -80,16 +117,17 @@ def _check_shapes(P, q, l_n=None, mu=None):
 
 
 # --------------------------------------------------------------------------- raw batched ops
-def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False):
-    """Batched solveQP on CUDA tensors: P (B,N,N), q (B,N,1) -> x (B,N,1) [, iters (B,) int32]."""
+def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None):
+    """Batched solveQP on CUDA tensors: P (B,N,N), q (B,N,1) -> x (B,N,1) [, iters (B,) int32].
+    warm_start (B,N,1), when given, is where the iteration starts (extension; None = the reference's behaviour)."""
     dev = P.device
     B, N = P.size(0), P.size(1)
     x = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
     iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
     L = _lib.load()
     with torch.cuda.device(dev):
-        rc = L.dq_qp_forward(_ptr(P), _ptr(q), None, _ptr(x), _ptr(iters), B, N, float(eps), float(mu_prox),
-                             int(max_iter), int(bool(adaptative_rho)), _stream_ptr(dev))
+        rc = L.dq_qp_forward(_ptr(P), _ptr(q), _ptr(warm_start), _ptr(x), _ptr(iters), B, N, float(eps), float(mu_prox),
+                             int(max_iter), _flags(adaptative_rho, warm_start), _stream_ptr(dev))
     _lib.check(rc, "dq_qp_forward")
     return (x, iters) if return_iters else x
 
@@ -108,15 +146,15 @@ def qp_backward(P, q, x, grad_x, need_P=True, need_q=True):
     return gP, gq
 
 
-def qcqp_forward(P, q, l_n, mu, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False):
+def qcqp_forward(P, q, l_n, mu, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None):
     dev = P.device
     B, N = P.size(0), P.size(1)
     x = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
     iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
     L = _lib.load()
     with torch.cuda.device(dev):
-        rc = L.dq_qcqp_forward(_ptr(P), _ptr(q), _ptr(l_n), _ptr(mu), None, _ptr(x), _ptr(iters), B, N,
-                               float(eps), float(mu_prox), int(max_iter), int(bool(adaptative_rho)),
+        rc = L.dq_qcqp_forward(_ptr(P), _ptr(q), _ptr(l_n), _ptr(mu), _ptr(warm_start), _ptr(x), _ptr(iters), B, N,
+                               float(eps), float(mu_prox), int(max_iter), _flags(adaptative_rho, warm_start),
                                _stream_ptr(dev))
     _lib.check(rc, "dq_qcqp_forward")
     return (x, iters) if return_iters else x
@@ -139,7 +177,8 @@ def qcqp_backward(P, q, l_n, mu, x, grad_x, need=(True, True, True, True)):
     return gP, gq, gl, gm
 
 
-def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, v=None, return_iters=False):
+def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, v=None, return_iters=False,
+                  warm_start=None):
     """Batched solveBoxQP (v is None) / solveSignedBoxQP on CUDA tensors: l_min, l_max[, v] are (B,N,1)."""
     dev = P.device
     B, N = P.size(0), P.size(1)
@@ -147,8 +186,9 @@ def boxqp_forward(P, q, l_min, l_max, eps, max_iter, mu_prox=1e-7, adaptative_rh
     iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
     L = _lib.load()
     with torch.cuda.device(dev):
-        rc = L.dq_boxqp_forward(_ptr(P), _ptr(q), _ptr(l_min), _ptr(l_max), _ptr(v), None, _ptr(x), _ptr(iters), B, N,
-                                float(eps), float(mu_prox), int(max_iter), int(bool(adaptative_rho)), _stream_ptr(dev))
+        rc = L.dq_boxqp_forward(_ptr(P), _ptr(q), _ptr(l_min), _ptr(l_max), _ptr(v), _ptr(warm_start), _ptr(x), _ptr(iters),
+                                B, N, float(eps), float(mu_prox), int(max_iter), _flags(adaptative_rho, warm_start),
+                                _stream_ptr(dev))
     _lib.check(rc, "dq_boxqp_forward")
     return (x, iters) if return_iters else x
 
@@ -182,7 +222,7 @@ class QPFn2(Function):
         _check_shapes(P, q)
         dev = _compute_device(P, q)
         Pd, qd = _as_dev(P, dev, "P"), _as_dev(q, dev, "q")
-        x = qp_forward(Pd, qd, eps, max_iter, mu_prox, True)
+        x = qp_forward(Pd, qd, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q))
         ctx.save_for_backward(Pd, qd, x)
         ctx.out_device = q.device
         return _back_to(x, q.device)
@@ -204,7 +244,7 @@ class QCQPFn2(Function):
         dev = _compute_device(P, q, l_n, mu)
         Pd, qd = _as_dev(P, dev, "P"), _as_dev(q, dev, "q")
         ld, md = _as_dev(l_n, dev, "l_n"), _as_dev(mu, dev, "mu")
-        x = qcqp_forward(Pd, qd, ld, md, eps, max_iter, mu_prox, True)
+        x = qcqp_forward(Pd, qd, ld, md, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q))
         ctx.save_for_backward(Pd, qd, ld, md, x)
         ctx.out_device = q.device
         return _back_to(x, q.device)
@@ -237,7 +277,7 @@ class BoxQPFn2(Function):
         _check_box(P, q, ("l_min", l_min), ("l_max", l_max))
         dev = _compute_device(P, q, l_min, l_max)
         t = [_as_dev(a, dev, n) for a, n in ((P, "P"), (q, "q"), (l_min, "l_min"), (l_max, "l_max"))]
-        x = boxqp_forward(*t, eps, max_iter, mu_prox, True)
+        x = boxqp_forward(*t, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q))
         ctx.save_for_backward(*t, x)
         ctx.out_device = q.device
         return _back_to(x, q.device)
@@ -260,7 +300,8 @@ class SignedBoxQPFn2(Function):
         _check_box(P, q, ("l_min", l_min), ("l_max", l_max), ("v", v))
         dev = _compute_device(P, q, l_min, l_max, v)
         t = [_as_dev(a, dev, n) for a, n in ((P, "P"), (q, "q"), (l_min, "l_min"), (l_max, "l_max"))]
-        x = boxqp_forward(*t, eps, max_iter, mu_prox, True, v=_as_dev(v, dev, "v"))
+        x = boxqp_forward(*t, eps, max_iter, mu_prox, True, v=_as_dev(v, dev, "v"),
+                          warm_start=_layer_warm(warm_start, dev, q))
         return _back_to(x, q.device)
 
     @staticmethod

@@ -49,11 +49,22 @@ int dq_last_cuda_error(void);         /* cudaError_t of the last DQ_ERR_CUDA on 
 int dq_max_n(void);                   /* DQ_MAX_N                                                 */
 
 /*
+ * Flag bits of the forward entry points' `adaptative_rho` argument.  0 / 1 are the reference's bool
+ * (pybindings.cpp:76-79).  DQ_FLAG_WARM_START is an extension, off by default because it
+ * changes results relative to the reference: the ADMM iteration then STARTS from warm_start (l_2 = l_2_pred =
+ * warm_start, u = -(P warm_start + q), q_prox = q - mu_prox warm_start) instead of from zero -- a handful of
+ * iterations when warm_start is the solution of a nearby problem (a simulator's previous time step).  The reference
+ * accepts warm_start and overwrites it before use (Solver.cpp:70 -> :80), so its results never depend on it.
+ */
+#define DQ_FLAG_ADAPTIVE_RHO 1
+#define DQ_FLAG_WARM_START 2
+
+/*
  * Forward ADMM solve of   min 1/2 x'Px + q'x  s.t. x >= 0      (Solver.cpp:61-123).
- *   warm_start : accepted for signature parity, never read -- the reference overwrites it before
- *                use (Solver.cpp:70 -> :80); may be NULL.
+ *   warm_start : (B,N).  Never read unless DQ_FLAG_WARM_START is set (see above); may be NULL otherwise.
  *   iters      : optional (B) int32 output, ADMM iterations executed per problem; may be NULL.
- *   eps, mu_prox, max_iter, adaptative_rho : as solveQP's arguments (pybindings.cpp:76).
+ *   eps, mu_prox, max_iter, adaptative_rho : as solveQP's arguments (pybindings.cpp:76); adaptative_rho also
+ *                carries the flag bits above.
  */
 int dq_qp_forward(const double* P, const double* q, const double* warm_start, double* x,
                   int32_t* iters, int64_t B, int32_t N, double eps, double mu_prox,

@@ -209,6 +209,12 @@ int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, 
 static int g_rho_nudge = 0;
 void dq_oracle_set_rho_nudge(int ulps) { g_rho_nudge = ulps; }
 
+/* Test hook: the `adaptative_rho` value the batched QP / QCQP forward wrappers pass down (default 1 = what qcqp.py
+ * passes, :27,:148).  3 = 1 | DQ_FLAG_WARM_START checks the warm-start extension of the CUDA library (not reference
+ * behaviour, see admm_solve_box). */
+static int g_batch_flags = 1;
+void dq_oracle_set_batch_flags(int flags) { g_batch_flags = flags; }
+
 /* ------------------------------------------------------------ ADMM core ------------------ */
 /* Shared skeleton of Solver::solveQP (Solver.cpp:61-123) and Solver::solveQCQP (:521-582).
  * radius == NULL selects the QP (non-negative clip, :82); otherwise the per-contact disk
@@ -250,6 +256,18 @@ static int admm_solve_box(const double* P_in, const double* q, const double* war
     l[i] = warm_start ? warm_start[i] : 0.0; /* :70/:529 -- dead: overwritten at :80/:539 */
     q_prox[i] = q[i];                        /* :74/:533 */
   }
+  /* NOT reference behaviour: the warm-start extension (flag bit 2 of adaptative_rho, DQ_FLAG_WARM_START in
+   * include/diffqcqp_b200.h) starts the iteration at warm_start.  Restated here only so that the extension has a
+   * CPU checker; with the bit clear (every reference call site) nothing below changes. */
+  if ((adaptative_rho & 2) && warm_start) {
+    gemv(P_in, warm_start, rhs, n);                       /* the multiplier of l = l_2 at a KKT point: u = -(P l + q) */
+    for (int i = 0; i < n; i++) {
+      l_2[i] = warm_start[i]; l_2_pred[i] = warm_start[i];
+      u[i] = -(rhs[i] + q[i]);
+      q_prox[i] = q[i] - mu_prox * warm_start[i];
+    }
+  }
+  adaptative_rho &= 1;
   double L = dq_oracle_power_iteration(P, n, is_qcqp ? 100 : 10);   /* :71 / :530 */
   double rho = sqrt(mu_prox * L) * pow(L / mu_prox, .4);            /* :72 / :531 */
   for (int k = 0; k < (g_rho_nudge < 0 ? -g_rho_nudge : g_rho_nudge); k++)   /* test hook, see dq_oracle_set_rho_nudge */
@@ -602,7 +620,7 @@ void dq_oracle_qp_forward_batch(const double* P, const double* q, const double* 
 #pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
   for (int64_t i = 0; i < B; i++) {
     int it = dq_oracle_solveQP(P + i * N * N, q + i * N, warm_start ? warm_start + i * N : NULL,
-                               x + i * N, N, eps, mu_prox, max_iter, 1);
+                               x + i * N, N, eps, mu_prox, max_iter, g_batch_flags);
     if (iters) iters[i] = it;
   }
 }
@@ -681,7 +699,7 @@ void dq_oracle_qcqp_forward_batch(const double* P, const double* q, const double
   for (int64_t i = 0; i < B; i++) {
     int it = dq_oracle_solveQCQP(P + i * N * N, q + i * N, l_n + i * nc, mu + i * nc,
                                  warm_start ? warm_start + i * N : NULL, x + i * N, N, eps,
-                                 mu_prox, max_iter, 1);
+                                 mu_prox, max_iter, g_batch_flags);
     if (iters) iters[i] = it;
   }
 }

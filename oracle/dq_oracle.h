@@ -84,6 +84,7 @@ int dq_oracle_iterative_refinement(const double* A, const double* b, double* x, 
 void dq_oracle_set_ir_force(int n);
 /* Test hook: start the ADMM with rho moved by `ulps` ulps (what a different libm pow() does to the reference). */
 void dq_oracle_set_rho_nudge(int ulps);
+void dq_oracle_set_batch_flags(int flags); /* test hook: 3 = adaptive rho + the warm-start extension */
 
 /* ---- batched entry points: the per-item loops of qcqp.py:22-52,141-181 in one C call ----
  * threads <= 0 means "all OpenMP threads"; threads == 1 is the reference's serial shape.

@@ -89,6 +89,8 @@ def lib():
         L.dq_oracle_set_ir_force.argtypes = [ctypes.c_int]
         L.dq_oracle_set_rho_nudge.restype = None
         L.dq_oracle_set_rho_nudge.argtypes = [ctypes.c_int]
+        L.dq_oracle_set_batch_flags.restype = None
+        L.dq_oracle_set_batch_flags.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -103,6 +105,12 @@ def _p(a):
 
 def max_threads() -> int:
     return int(lib().dq_oracle_max_threads())
+
+
+def set_batch_flags(flags: int) -> None:
+    """Test hook: 1 (default) = what qcqp.py passes; 3 = also start the ADMM iteration at warm_start (the CUDA
+    library's DQ_FLAG_WARM_START extension; NOT reference behaviour)."""
+    lib().dq_oracle_set_batch_flags(int(flags))
 
 
 def set_rho_nudge(ulps: int) -> None:

@@ -434,3 +434,43 @@ def test_oracle_box_backward(oracle):
             args[which][0, i, 0] -= 2 * d
             num = (up - f(*args)) / (2 * d)
             assert abs(num - grad[0, i, 0]) <= 2e-4 * max(1.0, abs(num)), (which, i, num, grad[0, i, 0])
+
+
+# ------------------------------------------------------------------ the warm-start extension's CPU checker (NOT reference behaviour)
+def test_warm_start_extension_checker(oracle):
+    """SURVEY.md 8(f) row 2.  The reference never reads warm_start (F2); the CUDA library has an opt-in flag that
+    starts the ADMM iteration there.  The oracle restates that extension behind a test hook so the kernels have a
+    CPU checker.  With the hook at its default the batched wrappers behave exactly as before."""
+    r = rng(21)
+    B, N = 256, 8
+    P = np.stack([np.diag(r.random(N) + 0.05) for _ in range(B)])
+    q = 2 * r.random((B, N, 1)) - 1
+    ws = r.random((B, N, 1))
+    x_cold, it_cold = oracle.qp_forward(P, q, None, 1e-8, 1000, return_iters=True)
+    x_dead, it_dead = oracle.qp_forward(P, q, ws, 1e-8, 1000, return_iters=True)          # default: dead (F2)
+    assert np.array_equal(x_cold, x_dead) and np.array_equal(it_cold, it_dead)
+    try:
+        oracle.set_batch_flags(3)
+        x1, it1 = oracle.qp_forward(P, q, x_cold, 1e-8, 1000, return_iters=True)             # start at the solution
+        assert it1.mean() <= 3 and np.abs(x1 - x_cold).max() <= 1e-4
+        q2 = q + 0.01 * r.standard_normal(q.shape)                                           # the next time step
+        oracle.set_batch_flags(1)
+        x2c, it2c = oracle.qp_forward(P, q2, None, 1e-8, 1000, return_iters=True)
+        oracle.set_batch_flags(3)
+        x2w, it2w = oracle.qp_forward(P, q2, x_cold, 1e-8, 1000, return_iters=True)
+        assert it2w.mean() < 0.75 * it2c.mean()
+        scale = np.maximum(1.0, np.abs(x2c).max(axis=(1, 2)))
+        assert (np.abs(x2w - x2c).max(axis=(1, 2)) <= 1e-4 * scale).all()  # both stop on the dual residual only (F3)
+        # QCQP: same hook
+        nc = N // 2
+        l_n, mu = 2 * r.random((B, nc, 1)), r.random((B, nc, 1))
+        oracle.set_batch_flags(1)
+        xq, itq = oracle.qcqp_forward(P, q, l_n, mu, None, 1e-8, 1000, return_iters=True)
+        xq2c, itq2c = oracle.qcqp_forward(P, q2, l_n, mu, None, 1e-8, 1000, return_iters=True)
+        oracle.set_batch_flags(3)
+        xq1, itq1 = oracle.qcqp_forward(P, q, l_n, mu, xq, 1e-8, 1000, return_iters=True)
+        assert itq1.mean() <= 3 and np.abs(xq1 - xq).max() <= 1e-5
+        xq2w, itq2w = oracle.qcqp_forward(P, q2, l_n, mu, xq, 1e-8, 1000, return_iters=True)
+        assert itq2w.mean() < 0.9 * itq2c.mean() and np.abs(xq2w - xq2c).max() <= 1e-5
+    finally:
+        oracle.set_batch_flags(1)

@@ -738,3 +738,69 @@ def test_forward_paths_bit_identical_variants(dq, wl, cuda_lib):
     for name, PP in (("diag", Pq), ("mixed", Pqm)):
         both(name + " qcqp", lambda: dq.qcqp_forward(*dev(PP, qq, l_n, mu), 1e-7, 1000, return_iters=True))
         both(name + " qcqp eps=1e-10", lambda: dq.qcqp_forward(*dev(PP, qq, l_n, mu), 1e-10, 1000, return_iters=True))
+
+
+# ------------------------------------------------------------------------------------ the warm-start extension
+@pytest.mark.parametrize("gen,B,N", [("qp_diag", 4099, 8), ("qp_dense", 1025, 8), ("qp_dense", 513, 16), ("qp_dense", 129, 32)])
+def test_warm_start_extension_qp(dq, wl, oracle, cuda_lib, gen, B, N):
+    """DQ_FLAG_WARM_START (off by default: the reference never reads warm_start, F2).  With the flag the iteration
+    starts at warm_start with the multiplier u = -(P warm_start + q): the kernel against the oracle's restatement of the
+    same extension (iteration counts equal, x within 10 eps), fewer iterations than the cold start, and the default
+    path unaffected by whatever warm_start holds."""
+    P, q, _ = getattr(wl, gen)(B, N, seed=700 + N)
+    g = torch.Generator().manual_seed(701)
+    q2 = q + 0.01 * torch.randn(q.shape, generator=g, dtype=torch.float64)      # "the next time step"
+    x_prev = dq.qp_forward(*dev(P, q), EPS, 1000)
+    x_cold, it_cold = dq.qp_forward(*dev(P, q2), EPS, 1000, return_iters=True)
+    x_dead, it_dead = dq.qp_forward(*dev(P, q2), EPS, 1000, return_iters=True)  # flag off: same bits whatever ws is
+    assert torch.equal(x_cold, x_dead) and torch.equal(it_cold, it_dead)
+    x_w, it_w = dq.qp_forward(*dev(P, q2), EPS, 1000, return_iters=True, warm_start=x_prev)
+    try:
+        oracle.set_batch_flags(3)
+        xo, ito = oracle.qp_forward(P.numpy(), q2.numpy(), x_prev.cpu().numpy(), EPS, 1000, return_iters=True)
+    finally:
+        oracle.set_batch_flags(1)
+    same = it_w.cpu().numpy() == ito
+    assert same.mean() >= (1.0 if gen == "qp_diag" else 0.995), same.mean()  # dense: FMA order of P ws differs in the last ulp
+    check_x(x_w[torch.from_numpy(same).cuda()], xo[same], EPS)
+    assert it_w.double().mean() < 0.8 * it_cold.double().mean(), (float(it_w.double().mean()), float(it_cold.double().mean()))
+    # started at its own answer the solver stops almost at once
+    x_again, it_again = dq.qp_forward(*dev(P, q2), EPS, 1000, return_iters=True, warm_start=x_w)
+    assert float(it_again.double().mean()) <= 0.4 * float(it_cold.double().mean())
+    # the layer reads warm_start only inside use_warm_start
+    import qcqp as ref_surface
+    from diffqcqp_b200.qcqp import use_warm_start
+    a = ref_surface.QPFn2.apply(P.cuda(), q2.cuda(), x_prev, EPS, 1000)
+    assert torch.equal(a, x_cold)
+    with use_warm_start(True):
+        b = ref_surface.QPFn2.apply(P.cuda(), q2.cuda(), x_prev, EPS, 1000)
+    assert torch.equal(b, x_w)
+    assert torch.equal(ref_surface.QPFn2.apply(P.cuda(), q2.cuda(), x_prev, EPS, 1000), x_cold)
+
+
+def test_warm_start_extension_qcqp_and_box(dq, wl, oracle):
+    B, N = 2050, 8
+    P, q, l_n, mu, _ = wl.qcqp_dense(B, N, seed=710)
+    g = torch.Generator().manual_seed(711)
+    q2 = q + 0.01 * torch.randn(q.shape, generator=g, dtype=torch.float64)
+    x_prev = dq.qcqp_forward(*dev(P, q, l_n, mu), EPS, 1000)
+    x_cold, it_cold = dq.qcqp_forward(*dev(P, q2, l_n, mu), EPS, 1000, return_iters=True)
+    x_w, it_w = dq.qcqp_forward(*dev(P, q2, l_n, mu), EPS, 1000, return_iters=True, warm_start=x_prev)
+    try:
+        oracle.set_batch_flags(3)
+        xo, ito = oracle.qcqp_forward(P.numpy(), q2.numpy(), l_n.numpy(), mu.numpy(), x_prev.cpu().numpy(), EPS, 1000,
+                                      return_iters=True)
+    finally:
+        oracle.set_batch_flags(1)
+    same = it_w.cpu().numpy() == ito
+    assert same.mean() >= 0.995
+    check_x(x_w[torch.from_numpy(same).cuda()], xo[same], EPS)
+    assert it_w.double().mean() < 0.9 * it_cold.double().mean()
+    assert float((x_w - x_cold).abs().max()) <= 1e-4   # the QCQP also tests the primal residual: both are at the optimum
+    # Box QP (diagonal, N = 8: the flag routes it to the generic kernel): a start at the answer stops at once
+    Pd, qd, _ = wl.qp_diag(1000, 8, seed=712)
+    lo, hi = -0.3 * torch.ones(1000, 8, 1, dtype=torch.float64), 0.2 * torch.ones(1000, 8, 1, dtype=torch.float64)
+    xb, itb = dq.boxqp_forward(*dev(Pd, qd, lo, hi), EPS, 1000, return_iters=True)
+    xb2, itb2 = dq.boxqp_forward(*dev(Pd, qd, lo, hi), EPS, 1000, return_iters=True, warm_start=xb)
+    assert float(itb2.double().mean()) <= 3.0 < float(itb.double().mean())
+    assert float((xb2 - xb).abs().max()) <= 1e-4
