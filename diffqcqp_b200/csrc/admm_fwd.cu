@@ -481,8 +481,11 @@ struct DiagRec {  // one problem's record in shared memory, in doubles
   static constexpr size_t bytes = (size_t)DIAG_CAP * D * sizeof(double) + DIAG_CAP * 8 + 16;
 };
 
+#ifndef DQ_DIAG_WPS
+#define DQ_DIAG_WPS 32  // resident warps per SM the QP variant's register budget is sized for
+#endif
 template <int PROX>
-__global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? 32 : 28) / DIAG_WARPS)
+__global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIAG_WPS : 28) / DIAG_WARPS)
     admm_fwd_diag8_kernel(const FwdParams p) {
   using R = DiagRec<PROX>;
   constexpr bool QCQP = (PROX == PROX_DISK);

@@ -1,5 +1,8 @@
 #!/bin/bash
 tag=${1:-v2}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_parity_gpu.py -q -k "warm_start" 2>&1 | grep -E "^E  .*|passed|failed" | cut -c1-300 | tee gpurun_out/${tag}_ws.txt
-timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -3 | cut -c1-300 | tee gpurun_out/${tag}_pytest_gpu.txt
+nvidia-smi topo -m 2>&1 | head -14 | tee gpurun_out/${tag}_topo.txt
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+for flag in "" "--no-numa"; do
+timeout 300 $TR --master-port 29531 bench.py --gpus 2 --steps 300 --warmup 10 $flag 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=2 $flag', d['value'], d['e2e'])" | tee -a gpurun_out/${tag}_numa.txt
+done
