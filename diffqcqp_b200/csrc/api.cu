@@ -111,7 +111,8 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
 // but is staged by the driver.  Measured: 84 MB per B=65536 N=8 step in 1.24-1.30 ms; this box's PCIe does
 // 0.97 ms for the same bytes as two bare concurrent copies (scripts/micro/pcie.py).  Tried and measured no better
 // (1.31-1.42 ms): tapered chunk sizes (small first / last chunk), per-chunk copies of the vectors on the P stream,
-// and the first chunk's vector slices ahead of the rest; more than 6 chunks is slower (1.33 ms at 8, 1.44 at 16).
+// the first chunk's vector slices ahead of the rest (on their own stream or on the P stream), and a small leading
+// chunk of 2048 / 4096 problems; more than 6 chunks is slower (1.33 ms at 8, 1.44 at 16).
 struct HostJob {
   bool qcqp;
   const double *P, *q, *l_n, *mu, *grad_x;
