@@ -330,7 +330,7 @@ def run_b200_arm(args):
     # one set = inputs (P, q, grad_l [, l_n, mu]) + outputs (x, grad_P, grad_q [, grad_l_n, grad_mu])
     in_bytes_per_set = 8 * B * (2 * N * N + 4 * N + (4 * nc if kind == "qcqp" else 0))
     R = max(2, int(-(-200e6 // in_bytes_per_set)) + 1)  # rotating sets: total footprint > 126 MB L2
-    R = min(R, 16)
+    R = min(max(R, args.streams), 16)  # at least one set per stream, so that overlapping steps never share buffers
     sets = []
     host0 = None
     for r in range(R):

@@ -1,8 +1,7 @@
 #!/bin/bash
 tag=${1:-v2}
 mkdir -p gpurun_out
-nvidia-smi topo -m 2>&1 | head -14 | tee gpurun_out/${tag}_topo.txt
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-for flag in "" "--no-numa"; do
-timeout 300 $TR --master-port 29531 bench.py --gpus 2 --steps 300 --warmup 10 $flag 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=2 $flag', d['value'], d['e2e'])" | tee -a gpurun_out/${tag}_numa.txt
+for v in "" scripts/variants/lib_wps28.so; do
+  DQ_LIB_PATH=$v python bench.py --steps 2000 --warmup 20 --no-cpu-baseline --no-e2e 2>/dev/null | \
+    python -c "import json,sys; d=json.loads(sys.stdin.read()); print('lib [$v]  ms/step %.4f  %.4g solves/s single-stream %.4f kernel_ms %s' % (d['ms_per_step'], d['value'], d['config']['single_stream_ms_per_step'], d['roofline']['kernel_ms']))" | tee -a gpurun_out/${tag}_wps.txt
 done
