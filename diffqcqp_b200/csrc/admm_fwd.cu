@@ -147,7 +147,7 @@ struct FwdTile {  // what one lane knows about its problem when the ADMM loop st
 // chain of iteration k.  When rho does change (a few times per solve) the speculative iteration is
 // recomputed with the new rho; when the tile stops it is dropped.  Results are identical to the
 // unpipelined order.  A finished tile keeps executing with its answer frozen until the warp is done.
-template <int T, int PROX, bool DENSE>
+template <int T, int PROX, bool DENSE, int R>
 __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t, double* Lb, double* db,
                                             double* vbuf, int& cur, int lane, int ti, int tile_base, int* it_out) {
   constexpr bool QCQP = (PROX == PROX_DISK);
@@ -158,7 +158,7 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
   double rho = t.rho, tau_inc = t.tau, tau_dec = t.tau;
   double mdiag = __dadd_rn(t.pdiag, __dadd_rn(rho, mu));  // P += (rho + mu) I   :75 / :534
   double irho = 1.0 / rho;
-  double pinv[T];      // dense: row ti of (P + (rho+mu) I)^-1 (dead when !DENSE)
+  double pinv[R];      // dense: row ti of (P + (rho+mu) I)^-1 (dead when !DENSE); R = row capacity, N <= R <= T
   double pinvd = 0.0;  // diagonal: its only non-zero entry
   bool live = t.vprob && p.max_iter > 0;
   bool refac = true;
@@ -178,7 +178,7 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
       vb[lane] = t.valid ? rhs : 0.0;
       __syncwarp();
       cur ^= 1;
-      l = row_dot<T>(pinv, vb + tile_base, N);
+      l = row_dot<R>(pinv, vb + tile_base, N);
     } else {
       l = __dmul_rn(pinvd, rhs);
     }
@@ -213,14 +213,14 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
   // against I give (1/s)(1/s), s = sqrt(m_ii)   :76-77, :100-101, :114-115
   auto refactor = [&]() {
     if constexpr (DENSE) {
-      double a[T];
-      load_row<T>(a, t.Prow, N, t.valid, t.vec32);  // L1/L2-resident re-read keeps the row out of the loop's registers
+      double a[R];
+      load_row<R>(a, t.Prow, N, t.valid, t.vec32);  // L1/L2-resident re-read keeps the row out of the loop's registers
 #pragma unroll
-      for (int j = 0; j < T; j++) {
+      for (int j = 0; j < R; j++) {
         if (j == ti) a[j] = mdiag;
         else if (j > ti) a[j] = 0.0;
       }
-      tile_spd_inverse<T>(a, pinv, Lb, db, N, ti, tile_base);
+      tile_spd_inverse<T, R>(a, pinv, Lb, db, N, ti, tile_base);
     } else {
       const double a = 1.0 / sqrt(mdiag);
       pinvd = __dmul_rn(a, a);
@@ -319,7 +319,7 @@ __device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t
 
 // One group (32/T consecutive problems starting at `first`, those below `bend`) solved by one warp: the whole
 // forward of the generic path.  wsm = this warp's FwdSmem<T>::per_warp_doubles of shared scratch.
-template <int T, int PROX>
+template <int T, int PROX, int R = T>
 __device__ __forceinline__ void solve_group(const FwdParams& p, long long first, long long bend, int lane,
                                             double* wsm) {
   constexpr bool QCQP = (PROX == PROX_DISK);
@@ -340,8 +340,8 @@ __device__ __forceinline__ void solve_group(const FwdParams& p, long long first,
   double* db = wsm + 32 * T + 64 + tile_base;  // [T] reciprocal pivots
 
   // ---- inputs straight into registers
-  double prow[T];
-  load_row<T>(prow, t.Prow, N, t.valid, t.vec32);
+  double prow[R];
+  load_row<R>(prow, t.Prow, N, t.valid, t.vec32);
   t.qi = t.valid ? __ldg(p.q + prob * N + ti) : 0.0;
   t.ws = (p.warm != nullptr && t.valid) ? __ldg(p.warm + prob * N + ti) : 0.0;
   t.radius = 0.0;
@@ -364,7 +364,7 @@ __device__ __forceinline__ void solve_group(const FwdParams& p, long long first,
   t.pdiag = 1.0;
   bool nz = false;
 #pragma unroll
-  for (int j = 0; j < T; j++) {
+  for (int j = 0; j < R; j++) {
     if (j == ti) t.pdiag = t.valid ? prow[j] : 1.0;
     else nz |= (prow[j] != 0.0);
   }
@@ -381,7 +381,7 @@ __device__ __forceinline__ void solve_group(const FwdParams& p, long long first,
     vb[lane] = v;
     __syncwarp();
     cur ^= 1;
-    return row_dot<T>(prow, vb + tile_base, N);
+    return row_dot<R>(prow, vb + tile_base, N);
   };
 
   t.u0 = 0.0;
@@ -418,13 +418,13 @@ __device__ __forceinline__ void solve_group(const FwdParams& p, long long first,
   }
 
   int it;
-  const double x = dense ? admm_loop<T, PROX, true>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it)
-                         : admm_loop<T, PROX, false>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it);
+  const double x = dense ? admm_loop<T, PROX, true, R>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it)
+                         : admm_loop<T, PROX, false, R>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it);
   if (t.valid) p.x[prob * N + ti] = x;
   if (t.vprob && ti == 0 && p.iters) p.iters[prob] = it;
 }
 
-template <int T, int PROX>
+template <int T, int PROX, int R>
 __global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : 16) / FWD_WARPS)
     admm_fwd_kernel(const FwdParams p) {
   constexpr int G = 32 / T;
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : 16) / FWD_WARPS
   const long long g = (long long)blockIdx.x * FWD_WARPS + warp;  // this warp's group
   if (g >= p.n_groups) return;
   double* wsm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * FwdSmem<T>::per_warp_doubles;
-  solve_group<T, PROX>(p, g * G, p.B, lane, wsm);
+  solve_group<T, PROX, R>(p, g * G, p.B, lane, wsm);
 }
 
 
@@ -814,12 +814,12 @@ __global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIA
   }
 }
 
-template <int T, int PROX>
+template <int T, int PROX, int R = T>
 static cudaError_t launch_fwd_t(const FwdParams& p, cudaStream_t stream) {
   static_assert(FwdSmem<T>::bytes <= 48 * 1024, "forward scratch must fit the default dynamic shared memory limit");
   const long long grid = (p.n_groups + FWD_WARPS - 1) / FWD_WARPS;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  admm_fwd_kernel<T, PROX><<<(unsigned)grid, FWD_WARPS * 32, FwdSmem<T>::bytes, stream>>>(p);
+  admm_fwd_kernel<T, PROX, R><<<(unsigned)grid, FWD_WARPS * 32, FwdSmem<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -828,7 +828,8 @@ static cudaError_t launch_fwd_p(const FwdParams& p, int T, cudaStream_t stream) 
   switch (T) {
     case 8: return launch_fwd_t<8, PROX>(p, stream);
     case 16: return launch_fwd_t<16, PROX>(p, stream);
-    default: return launch_fwd_t<32, PROX>(p, stream);
+    default:  // 32 lanes per problem; rows of up to 24 entries run the instance unrolled to 24 (see tile_spd_inverse)
+      return p.N <= 24 ? launch_fwd_t<32, PROX, 24>(p, stream) : launch_fwd_t<32, PROX>(p, stream);
   }
 }
 

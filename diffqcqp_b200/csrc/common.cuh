@@ -39,12 +39,15 @@ __device__ __forceinline__ double tile_sum(double v) {
 // drops into its slow path for the zero numerators of the padded / upper-triangular lanes.  The dot
 // products run on two interleaved FMA accumulators.  Differences from the reference's divide-by-pivot
 // are at rounding level, like Eigen's own blocked evaluation order.
-template <int T>
-__device__ __forceinline__ void tile_spd_inverse(double (&a)[T], double (&out)[T], double* Lb, double* dinv,
+// R <= T is the row capacity the loops are unrolled to (N <= R): a 32-lane tile with N <= 24 runs the R = 24 instance,
+// 44 % fewer unrolled triangular-loop instructions and 16 fewer registers per array (the T = 32 forward is
+// instruction-fetch bound, profiles/r01_qcqp_n24_ncu_lines.txt: no_inst 37 % of the stall samples).
+template <int T, int R = T>
+__device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R], double* Lb, double* dinv,
                                                  int N, int ti, int tile_base_lane) {
   // ---- Cholesky, left-looking, one column per step (Eigen LLT unblocked order)
 #pragma unroll
-  for (int k = 0; k < T; k++) {
+  for (int k = 0; k < R; k++) {
     if (k < N) {
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
@@ -68,7 +71,7 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[T], double (&out)[T
   }
   // ---- forward substitution L y = e_ti
 #pragma unroll
-  for (int i = 0; i < T; i++) {
+  for (int i = 0; i < R; i++) {
     if (i < N) {
       double acc0 = (i == ti) ? 1.0 : 0.0, acc1 = 0.0;
 #pragma unroll
@@ -84,15 +87,15 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[T], double (&out)[T
   }
   // ---- back substitution L^T x = y   (L^T(i,j) = L(j,i) = Lb[i][j] for j > i)
 #pragma unroll
-  for (int i = T - 1; i >= 0; i--) {
+  for (int i = R - 1; i >= 0; i--) {
     if (i < N) {
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-      for (int j = i + 1; j + 1 < T; j += 2) {
+      for (int j = i + 1; j + 1 < R; j += 2) {
         acc0 = fma(Lb[i * T + j], out[j], acc0);
         acc1 = fma(Lb[i * T + j + 1], out[j + 1], acc1);
       }
-      if ((T - 1 - i) & 1) acc0 = fma(Lb[i * T + T - 1], out[T - 1], acc0);
+      if ((R - 1 - i) & 1) acc0 = fma(Lb[i * T + R - 1], out[R - 1], acc0);
       out[i] = (out[i] - (acc0 + acc1)) * dinv[i];
     }
   }

@@ -1,7 +1,7 @@
 #!/bin/bash
 tag=${1:-v2}
 mkdir -p gpurun_out
-for v in "" scripts/variants/lib_wps28.so; do
-  DQ_LIB_PATH=$v python bench.py --steps 2000 --warmup 20 --no-cpu-baseline --no-e2e 2>/dev/null | \
-    python -c "import json,sys; d=json.loads(sys.stdin.read()); print('lib [$v]  ms/step %.4f  %.4g solves/s single-stream %.4f kernel_ms %s' % (d['ms_per_step'], d['value'], d['config']['single_stream_ms_per_step'], d['roofline']['kernel_ms']))" | tee -a gpurun_out/${tag}_wps.txt
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -3 | cut -c1-300 | tee gpurun_out/${tag}_pytest_gpu.txt
+for w in qcqp_n24 qp_dense_n32; do
+python bench.py --workload $w --steps 20 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['config']['name'], d['ms_per_step'], d['roofline']['kernel_ms'])" | tee -a gpurun_out/${tag}_bench.txt
 done
