@@ -39,3 +39,11 @@ for N, B, diag in ((8, 21, False), (8, 21, True), (6, 7, False), (16, 9, False),
     P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=N, diag=diag)
     a = [t.cuda() for t in (P, q, l_n, mu)]
     run(f"qcqp N={N} diag={diag}", lambda: dq.qcqp_backward(*a, dq.qcqp_forward(*a, 1e-7, 200), g.cuda()))
+
+# the warm-start extension (generic kernel, diagonal and dense)
+P, q, g = wl.qp_dense(33, 8, seed=5)
+x0 = dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 200)
+run("warm start qp dense N=8", lambda: dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 200, warm_start=x0))
+P, q, g = wl.qp_diag(33, 8, seed=6)
+x0 = dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 200)
+run("warm start qp diag N=8", lambda: dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 200, warm_start=x0))
