@@ -435,6 +435,29 @@ def run_b200_arm(args):
         fwd_ms.append(e[0].elapsed_time(e[1])); bwd_ms.append(e[1].elapsed_time(e[2]))
     fwd_avg, bwd_avg = sum(fwd_ms) / len(fwd_ms), sum(bwd_ms) / len(bwd_ms)
 
+    # ---- sustained per-launch cost of each kernel: the same launches back to back, round-robin on the S streams (what a
+    # launch costs when the next batch's work fills the GPU behind its stragglers, as in the timed region)
+    def sustained(fn, n=200):
+        nonlocal sp
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(e0)
+        for k in range(n):
+            sp = sps[k % S]
+            fn(sets[k % R])
+        sp = sps[0]
+        for st in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(st)
+            streams[0].wait_event(e)
+        e1.record(streams[0])
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    sustained(fwd, 20)
+    fwd_sus, bwd_sus = sustained(fwd), sustained(bwd)
+
     # ---- e2e through the host-buffer C-ABI entry point
     e2e = None
     if not args.no_e2e:
@@ -514,9 +537,9 @@ def run_b200_arm(args):
                         "note": "rank 0 scatters (P,q,grad_l[,l_n,mu]) over NCCL send/recv, every rank solves its shard, x* and grad_q are gathered on rank 0"}
 
     if distributed:
-        t = torch.tensor([total_ms, fwd_avg, bwd_avg], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, fwd_avg, bwd_avg, fwd_sus, bwd_sus], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, fwd_avg, bwd_avg = [float(v) for v in t.tolist()]
+        total_ms, fwd_avg, bwd_avg, fwd_sus, bwd_sus = [float(v) for v in t.tolist()]
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -546,11 +569,17 @@ def run_b200_arm(args):
                          "alg_bytes_per_solve": {"fwd": fb, "bwd": bb},
                          "kernel_ms": {"fwd": fwd_avg, "bwd": bwd_avg},
                          "kernel_frac": {"fwd": fb * B / (fwd_avg * 1e-3) / 1e9 / peak, "bwd": bb * B / (bwd_avg * 1e-3) / 1e9 / peak},
+                         "kernel_ms_sustained": {"fwd": fwd_sus, "bwd": bwd_sus},
+                         "kernel_frac_sustained": {"fwd": fb * B / (fwd_sus * 1e-3) / 1e9 / peak,
+                                                   "bwd": bb * B / (bwd_sus * 1e-3) / 1e9 / peak},
                          "step_achieved_gbs": step_achieved, "step_frac": step_achieved / peak,
                          "overlapped_step_ms": total_ms / args.steps,
                          "note": "the forward kernel is FP64-issue/latency bound, not HBM bound (DESIGN.md section 5.1); "
-                                 "kernel_ms are isolated launches on one stream (they include the launch's straggler tail, "
-                                 "which the timed region overlaps with the next batch's work)"},
+                                 "achieved / frac / kernel_ms are isolated launches on one stream (they include the launch's "
+                                 "straggler tail); kernel_ms_sustained are the same launches back to back on the timed "
+                                 "region's streams, where the next batch's work fills the GPU behind the stragglers (for the "
+                                 "HBM-bound backward that figure also overlaps one launch's write-back with the next launch, "
+                                 "so its fraction can exceed 1)"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (the reference arm covers N>1)
