@@ -33,11 +33,14 @@ struct BwdQcqpSmem {
 #ifndef DQ_QCQP_BWD_MINB32
 #define DQ_QCQP_BWD_MINB32 4
 #endif
-template <int T>
+// R = row capacity (N <= R <= T): register arrays and unrolled loops stop at R; a 32-lane tile with N <= 24 runs R = 24
+// (fewer registers, a third less unrolled code; results are the same bits, the skipped terms are exact zeros).
+template <int T, int R>
 __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP_BWD_MINB32 : (T == 16 ? 6 : 4)))
     qcqp_bwd_kernel(const BwdParams p) {
   constexpr int G = 32 / T;
   constexpr int T2 = T / 2;
+  constexpr int R2 = R / 2;
   constexpr int WS = BwdQcqpSmem<T>::WS;
   constexpr int WARPS = BwdQcqpSmem<T>::WARPS;
   constexpr double MU_IR = 1e-7, EPS_IR = 1e-10;  // Solver.cpp:15
@@ -90,21 +93,21 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     const double muc = valid ? __ldg(p.mu + prob * nc + c) : 0.0;
     const double rc = lnc * muc;  // mul_n  pybindings.cpp:66
 
-    double drow[T];  // row ti of P, then of D = P + blkdiag(2 gamma_c I2)
+    double drow[R];  // row ti of P, then of D = P + blkdiag(2 gamma_c I2)
     {
       const double* src = p.P + (prob * N + ti) * N;
 #pragma unroll
-      for (int j = 0; j < T; j++) drow[j] = 0.0;
+      for (int j = 0; j < R; j++) drow[j] = 0.0;
       if (valid) {
-        if (N == T && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0) {
+        if (N == R && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0) {
 #pragma unroll
-          for (int j = 0; j < T; j += 4)
+          for (int j = 0; j < R; j += 4)
             asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
                          : "=d"(drow[j]), "=d"(drow[j + 1]), "=d"(drow[j + 2]), "=d"(drow[j + 3])
                          : "l"(src + j));
         } else {
 #pragma unroll
-          for (int j = 0; j < T; j++)
+          for (int j = 0; j < R; j++)
             if (j < N) drow[j] = __ldg(src + j);
         }
       }
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     double pd = 0.0;
     bool nzoff = false;
 #pragma unroll
-    for (int j = 0; j < T; j++) {
+    for (int j = 0; j < R; j++) {
       if (j == ti) pd = drow[j];
       else nzoff |= (drow[j] != 0.0);
     }
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     // ---- dualFromPrimalQCQP (Solver.cpp:584-617)
     vb[ti] = li;
     __syncwarp();
-    const double g0 = tile_row_dot<T>(drow, vb, N) + qi;  // (P l + q)_i
+    const double g0 = tile_row_dot<R>(drow, vb, N) + qi;  // (P l + q)_i
     __syncwarp();
     const double lo = __shfl_xor_sync(FULL_MASK, li, 1);
     const double g0o = __shfl_xor_sync(FULL_MASK, g0, 1);
@@ -226,10 +229,10 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       }
     } else {
 #pragma unroll
-    for (int j = 0; j < T; j++)
+    for (int j = 0; j < R; j++)
       if (j == ti) drow[j] = 2 * gamma + drow[j];  // D_tild = D_tild + P  :656
 #pragma unroll
-    for (int j = 0; j < T; j++) Db[ti * T + j] = drow[j];
+    for (int j = 0; j < R; j++) Db[ti * T + j] = drow[j];
     if (even) {
       cb0[c] = act ? slack : 0.0;
       cb1[c] = act ? bt0 : 0.0;
@@ -238,11 +241,11 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     }
     vb[ti] = gi;
     __syncwarp();
-    const double rhs2 = tile_row_dot<T>(drow, vb, N);  // (D grad_l)_i
+    const double rhs2 = tile_row_dot<R>(drow, vb, N);  // (D grad_l)_i
     // A21 row ti and L21 row ti
-    double cv[T2], wv[T2];
+    double cv[R2], wv[R2];
 #pragma unroll
-    for (int cc = 0; cc < T2; cc++) {
+    for (int cc = 0; cc < R2; cc++) {
       double v = fma(drow[2 * cc], cb1[cc], drow[2 * cc + 1] * cb2[cc]);
       if (cc == c) v += (2 * li) * cb0[cc];
       cv[cc] = v;
@@ -250,13 +253,13 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       Wb[ti * WS + cc] = wv[cc];
     }
     // A22 row ti = (D D^T + Ct Ct^T + mu I)(ti,:)
-    double a22[T];
+    double a22[R];
 #pragma unroll
-    for (int j = 0; j < T; j++) {
+    for (int j = 0; j < R; j++) {
       double acc = 0.0;
       if (j < N) {
 #pragma unroll
-        for (int k = 0; k < T; k += 2) {
+        for (int k = 0; k < R; k += 2) {
           double2 m = *reinterpret_cast<const double2*>(Db + j * T + k);
           acc = fma(drow[k], m.x, acc);
           acc = fma(drow[k + 1], m.y, acc);
@@ -265,28 +268,28 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       a22[j] = acc;
     }
 #pragma unroll
-    for (int j = 0; j < T; j++) {
+    for (int j = 0; j < R; j++) {
       if (act && (j >> 1) == c) a22[j] += (2 * li) * ((j == ti) ? (2 * li) : (2 * lo));
       if (j == ti) a22[j] += MU_IR;
     }
     __syncwarp();  // all lanes finished reading Db (D rows) and wrote Wb
 #pragma unroll
-    for (int j = 0; j < T; j++) Db[ti * T + j] = valid ? a22[j] : 0.0;  // Db now holds A22 (symmetric)
+    for (int j = 0; j < R; j++) Db[ti * T + j] = valid ? a22[j] : 0.0;  // Db now holds A22 (symmetric)
     // Schur complement row: sc(ti,j) = A22(ti,j) - sum_c L21(ti,c) L21(j,c)
-    double scinv[T];
+    double scinv[R];
     {
-      double a[T];
+      double a[R];
 #pragma unroll
-      for (int j = 0; j < T; j++) {
+      for (int j = 0; j < R; j++) {
         double acc = 0.0;
         if (j < N) {
 #pragma unroll
-          for (int cc = 0; cc < T2; cc++) acc = fma(wv[cc], Wb[j * WS + cc], acc);
+          for (int cc = 0; cc < R2; cc++) acc = fma(wv[cc], Wb[j * WS + cc], acc);
         }
         a[j] = (valid && j <= ti) ? (a22[j] - acc) : 0.0;
       }
       __syncwarp();
-      tile_spd_inverse<T>(a, scinv, Lb, db, N, ti, tile_base);
+      tile_spd_inverse<T, R>(a, scinv, Lb, db, N, ti, tile_base);
     }
 
     // ---- block solve  [b1; b2] = AA^-1 [t1; t2]   (t1, b1 per contact on the lane pair; t2, b2 per lane)
@@ -296,10 +299,10 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       __syncwarp();
       double acc = 0.0;
 #pragma unroll
-      for (int cc = 0; cc < T2; cc++) acc = fma(wv[cc], cb0[cc], acc);
+      for (int cc = 0; cc < R2; cc++) acc = fma(wv[cc], cb0[cc], acc);
       vb[ti] = valid ? (t2 - acc) : 0.0;  // t2 - L21 y1
       __syncwarp();
-      b2 = tile_row_dot<T>(scinv, vb, N);  // Schur^-1 (...)
+      b2 = tile_row_dot<R>(scinv, vb, N);  // Schur^-1 (...)
       __syncwarp();
       vb[ti] = b2;
       __syncwarp();
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       __syncwarp();
       double acc = 0.0;
 #pragma unroll
-      for (int cc = 0; cc < T2; cc++) acc = fma(cv[cc], cb0[cc], acc);  // A21 x1
+      for (int cc = 0; cc < R2; cc++) acc = fma(cv[cc], cb0[cc], acc);  // A21 x1
       double acc2 = 0.0, acc3 = 0.0;
       for (int i = 0; i < N; i++) {
         const double xv = vb[i];
@@ -367,9 +370,9 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
         double* out = p.grad_P + (prob * N + ti) * N;
         const double* xr = xb + tile_base;
         const double ndl = -dl;
-        if (N == T && (reinterpret_cast<uintptr_t>(p.grad_P) & 31u) == 0) {
+        if (N == R && (reinterpret_cast<uintptr_t>(p.grad_P) & 31u) == 0) {
 #pragma unroll
-          for (int j = 0; j < T; j += 4) {
+          for (int j = 0; j < R; j += 4) {
             const double2 x01 = *reinterpret_cast<const double2*>(xr + j);
             const double2 x23 = *reinterpret_cast<const double2*>(xr + j + 2);
             asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(out + j), "d"(ndl * x01.x), "d"(ndl * x01.y),
@@ -384,13 +387,13 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
   }
 }
 
-template <int T>
+template <int T, int R = T>
 static cudaError_t launch_qcqp_bwd_t(const BwdParams& p, cudaStream_t stream) {
   static_assert(BwdQcqpSmem<T>::bytes <= 48 * 1024, "backward scratch must fit the default dynamic shared memory limit");
   constexpr int WARPS = BwdQcqpSmem<T>::WARPS;
   const long long grid = (p.n_groups + WARPS - 1) / WARPS;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  qcqp_bwd_kernel<T><<<(unsigned)grid, WARPS * 32, BwdQcqpSmem<T>::bytes, stream>>>(p);
+  qcqp_bwd_kernel<T, R><<<(unsigned)grid, WARPS * 32, BwdQcqpSmem<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -398,7 +401,7 @@ cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, cudaStream_t stream) {
   switch (T) {
     case 8: return launch_qcqp_bwd_t<8>(p, stream);
     case 16: return launch_qcqp_bwd_t<16>(p, stream);
-    default: return launch_qcqp_bwd_t<32>(p, stream);
+    default: return p.N <= 24 ? launch_qcqp_bwd_t<32, 24>(p, stream) : launch_qcqp_bwd_t<32>(p, stream);
   }
 }
 
