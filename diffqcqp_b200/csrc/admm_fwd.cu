@@ -427,8 +427,11 @@ __device__ __forceinline__ void solve_group(const FwdParams& p, long long first,
 #ifndef DQ_FWD_WPS24
 #define DQ_FWD_WPS24 16  // resident warps per SM the 32-lane, 24-entry instance is sized for
 #endif
+#ifndef DQ_FWD_WPS16
+#define DQ_FWD_WPS16 16  // resident warps per SM the 16-lane instance is sized for
+#endif
 template <int T, int PROX, int R>
-__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : ((T == 32 && R == 24) ? DQ_FWD_WPS24 : 16)) / FWD_WARPS)
+__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : ((T == 32 && R == 24) ? DQ_FWD_WPS24 : (T == 16 ? DQ_FWD_WPS16 : 16))) / FWD_WARPS)
     admm_fwd_kernel(const FwdParams p) {
   constexpr int G = 32 / T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
