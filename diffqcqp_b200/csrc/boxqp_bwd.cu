@@ -58,7 +58,8 @@ __device__ __forceinline__ Inv2 spd2(double a00, double a10, double a11) {
   return o;
 }
 
-template <int T>
+// R = row capacity (N <= R <= T): register arrays and unrolled loops stop at R (a 32-lane tile with N <= 24 runs R = 24).
+template <int T, int R>
 __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(const BoxBwdParams p) {
   constexpr int G = 32 / T;
   constexpr int WARPS = BwdBoxSmem<T>::WARPS;
@@ -92,21 +93,21 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
   __syncwarp();
 
   // ---- inputs straight into registers
-  double prow[T];
+  double prow[R];
   {
     const double* src = p.P + (prob * N + ti) * N;
 #pragma unroll
-    for (int j = 0; j < T; j++) prow[j] = 0.0;
+    for (int j = 0; j < R; j++) prow[j] = 0.0;
     if (valid) {
-      if (N == T && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0) {
+      if (N == R && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0) {
 #pragma unroll
-        for (int j = 0; j < T; j += 4)
+        for (int j = 0; j < R; j += 4)
           asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
                        : "=d"(prow[j]), "=d"(prow[j + 1]), "=d"(prow[j + 2]), "=d"(prow[j + 3])
                        : "l"(src + j));
       } else {
 #pragma unroll
-        for (int j = 0; j < T; j++)
+        for (int j = 0; j < R; j++)
           if (j < N) prow[j] = __ldg(src + j);
       }
     }
@@ -117,13 +118,13 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
   const double lmin = valid ? __ldg(p.l_min + prob * N + ti) : 0.0;
   const double lmax = valid ? __ldg(p.l_max + prob * N + ti) : 0.0;
 #pragma unroll
-  for (int j = 0; j < T; j++) Pb[ti * T + j] = prow[j];
+  for (int j = 0; j < R; j++) Pb[ti * T + j] = prow[j];
 
   // y = P v (row ti) and z = P^T v (column ti; Pb read column-wise: lanes hit consecutive words)
   auto gemv_P = [&](double v) -> double {
     vb[ti] = v;
     __syncwarp();
-    const double r = tile_row_dot<T>(prow, vb, N);
+    const double r = tile_row_dot<R>(prow, vb, N);
     __syncwarp();
     return r;
   };
@@ -196,17 +197,17 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
   const double nact = (lowA ? 1.0 : 0.0) + (upA ? 1.0 : 0.0);                      // (Id2 Id2^T)(i,i)
 
   // A22 row ti = (Id2 Id2^T + P P^T + mu I)(ti,:), Schur row = A22 - sum_i w_i P(ti,i) P(:,i)
-  double scinv[T];
+  double scinv[R];
   {
     wb[ti] = alpha_lo * alpha_lo + alpha_up * alpha_up;
     __syncwarp();
-    double a22[T], a[T];
+    double a22[R], a[R];
 #pragma unroll
-    for (int j = 0; j < T; j++) {
+    for (int j = 0; j < R; j++) {
       double acc = 0.0, accw = 0.0;
       if (j < N) {
 #pragma unroll
-        for (int k = 0; k < T; k += 2) {
+        for (int k = 0; k < R; k += 2) {
           const double2 m = *reinterpret_cast<const double2*>(Pb + j * T + k);
           const double2 w = *reinterpret_cast<const double2*>(wb + k);
           acc = fma(prow[k], m.x, acc);
@@ -220,14 +221,14 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
       a[j] = (valid && j <= ti) ? (acc - accw) : 0.0;
     }
 #pragma unroll
-    for (int j = 0; j < T; j++) Db[ti * T + j] = valid ? a22[j] : 0.0;
+    for (int j = 0; j < R; j++) Db[ti * T + j] = valid ? a22[j] : 0.0;
     if (!valid) {
 #pragma unroll
-      for (int j = 0; j < T; j++)
+      for (int j = 0; j < R; j++)
         if (j == ti) a[j] = 1.0;  // padded lanes: identity (never read: tile_spd_inverse stops at N)
     }
     __syncwarp();
-    tile_spd_inverse<T>(a, scinv, Lb, db, N, ti, tile_base);
+    tile_spd_inverse<T, R>(a, scinv, Lb, db, N, ti, tile_base);
   }
 
   // [b1; b2] = AA^-1 [t1; t2]   (t1, b1: this element's two constraint slots; t2, b2: this element)
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
     const double pe = gemv_P(alpha_lo * y_lo + alpha_up * y_up);       // L21 y1 = P e
     vb[ti] = valid ? (t2 - pe) : 0.0;
     __syncwarp();
-    b2 = tile_row_dot<T>(scinv, vb, N);                                // Schur^-1 (t2 - L21 y1)
+    b2 = tile_row_dot<R>(scinv, vb, N);                                // Schur^-1 (t2 - L21 y1)
     __syncwarp();
     const double z = gemv_Pt(b2);                                      // (P^T b2)_i ; L21^T b2 = alpha z
     const double u_lo = y_lo - alpha_lo * z, u_up = y_up - alpha_up * z;
@@ -293,9 +294,9 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
     if (valid) {
       double* out = p.grad_P + (prob * N + ti) * N;
       const double ndl = -dl;
-      if (N == T && (reinterpret_cast<uintptr_t>(p.grad_P) & 31u) == 0) {
+      if (N == R && (reinterpret_cast<uintptr_t>(p.grad_P) & 31u) == 0) {
 #pragma unroll
-        for (int j = 0; j < T; j += 4) {
+        for (int j = 0; j < R; j += 4) {
           const double2 x01 = *reinterpret_cast<const double2*>(xb + j);
           const double2 x23 = *reinterpret_cast<const double2*>(xb + j + 2);
           asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(out + j), "d"(ndl * x01.x), "d"(ndl * x01.y),
@@ -309,13 +310,13 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
   }
 }
 
-template <int T>
+template <int T, int R = T>
 static cudaError_t launch_boxqp_bwd_t(const BoxBwdParams& p, cudaStream_t stream) {
   constexpr int WARPS = BwdBoxSmem<T>::WARPS;
   static_assert(BwdBoxSmem<T>::bytes <= 48 * 1024, "backward scratch must fit the default dynamic shared memory limit");
   const long long grid = (p.n_groups + WARPS - 1) / WARPS;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  boxqp_bwd_kernel<T><<<(unsigned)grid, WARPS * 32, BwdBoxSmem<T>::bytes, stream>>>(p);
+  boxqp_bwd_kernel<T, R><<<(unsigned)grid, WARPS * 32, BwdBoxSmem<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -323,7 +324,7 @@ cudaError_t launch_boxqp_bwd(const BoxBwdParams& p, int T, cudaStream_t stream) 
   switch (T) {
     case 8: return launch_boxqp_bwd_t<8>(p, stream);
     case 16: return launch_boxqp_bwd_t<16>(p, stream);
-    default: return launch_boxqp_bwd_t<32>(p, stream);
+    default: return p.N <= 24 ? launch_boxqp_bwd_t<32, 24>(p, stream) : launch_boxqp_bwd_t<32>(p, stream);
   }
 }
 

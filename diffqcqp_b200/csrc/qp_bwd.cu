@@ -47,7 +47,8 @@ __device__ __forceinline__ void load_row_bwd(double (&row)[T], const double* __r
   }
 }
 
-template <int T>
+// R = row capacity (N <= R <= T): register arrays and unrolled loops stop at R (a 32-lane tile with N <= 24 runs R = 24).
+template <int T, int R>
 __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 16 ? 4 : 6))) qp_bwd_kernel(const BwdParams p) {
   constexpr int G = 32 / T;
   constexpr int WARPS = BwdQpCfg<T>::WARPS;
@@ -75,15 +76,15 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
 
   // ---- inputs straight into registers
   const bool vecP = (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0;
-  double prow[T];
-  load_row_bwd<T>(prow, p.P + (prob * N + ti) * N, N, valid, vecP);
+  double prow[R];
+  load_row_bwd<R>(prow, p.P + (prob * N + ti) * N, N, valid, vecP);
   const double qi = valid ? __ldg(p.q + prob * N + ti) : 0.0;
   const double xi = valid ? __ldg(p.x + prob * N + ti) : 0.0;
   const double gi = valid ? __ldg(p.grad_x + prob * N + ti) : 0.0;
   double pdiag = 1.0;
   bool nz = false;
 #pragma unroll
-  for (int j = 0; j < T; j++) {
+  for (int j = 0; j < R; j++) {
     if (j == ti) pdiag = valid ? prow[j] : 1.0;
     else nz |= (prow[j] != 0.0);
   }
@@ -122,27 +123,27 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
     __syncwarp();
     vb[ti] = xi;
     __syncwarp();
-    const double Pl = tile_row_dot<T>(prow, vb, N);
+    const double Pl = tile_row_dot<R>(prow, vb, N);
     __syncwarp();
     double gamma = -(Pl + qi);
     if (xi > EPS_ACT) gamma = 0.0;
     const bool act = valid && (gamma < -1e-10);
     const bool fr = valid && !act;
     const unsigned fmask = (__ballot_sync(FULL_MASK, fr) >> tile_base) & (T == 32 ? 0xffffffffu : ((1u << T) - 1u));
-    double aa[T];
-    double pm[T];
+    double aa[R];
+    double pm[R];
 #pragma unroll
-    for (int j = 0; j < T; j++) pm[j] = (fr && ((fmask >> j) & 1u)) ? prow[j] : 0.0;
+    for (int j = 0; j < R; j++) pm[j] = (fr && ((fmask >> j) & 1u)) ? prow[j] : 0.0;
 #pragma unroll
-    for (int j = 0; j < T; j++) Mb[ti * T + j] = pm[j];
+    for (int j = 0; j < R; j++) Mb[ti * T + j] = pm[j];
     __syncwarp();
     // AA(i,j) = sum_k Pm(i,k) Pm(j,k)   (P_ff P_ff^T; zero rows/cols for active indices)
 #pragma unroll
-    for (int j = 0; j < T; j++) {
+    for (int j = 0; j < R; j++) {
       double acc = 0.0;
       if (j < N) {
 #pragma unroll
-        for (int k = 0; k < T; k += 2) {
+        for (int k = 0; k < R; k += 2) {
           const double2 m = *reinterpret_cast<const double2*>(Mb + j * T + k);
           acc = fma(pm[k], m.x, acc);
           acc = fma(pm[k + 1], m.y, acc);
@@ -153,19 +154,19 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
     // Ab = P_ff g_f
     vb[ti] = fr ? gi : 0.0;
     __syncwarp();
-    const double abv = tile_row_dot<T>(pm, vb, N);
+    const double abv = tile_row_dot<R>(pm, vb, N);
     __syncwarp();
     // diagonal: active rows hold l_i^2, everyone gets + mu_ir
 #pragma unroll
-    for (int j = 0; j < T; j++)
+    for (int j = 0; j < R; j++)
       if (j == ti) aa[j] = (act ? xi * xi : aa[j]) + MU_IR;
-    double a[T], ainv[T];
+    double a[R], ainv[R];
 #pragma unroll
-    for (int j = 0; j < T; j++) a[j] = (valid && j <= ti) ? aa[j] : 0.0;
-    tile_spd_inverse<T>(a, ainv, Lb, db, N, ti, tile_base);
+    for (int j = 0; j < R; j++) a[j] = (valid && j <= ti) ? aa[j] : 0.0;
+    tile_spd_inverse<T, R>(a, ainv, Lb, db, N, ti, tile_base);
     vb[ti] = valid ? abv : 0.0;
     __syncwarp();
-    const double w = tile_row_dot<T>(ainv, vb, N);  // AA_tild_inv * Ab  :27
+    const double w = tile_row_dot<R>(ainv, vb, N);  // AA_tild_inv * Ab  :27
     __syncwarp();
     double x = 0.0, res_pred = 1.7976931348623157e308;
     int ni = 0;
@@ -174,12 +175,12 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
       if (!__any_sync(FULL_MASK, !irdone)) break;
       vb[ti] = x;
       __syncwarp();
-      const double t = tile_row_dot<T>(ainv, vb, N);
+      const double t = tile_row_dot<R>(ainv, vb, N);
       __syncwarp();
       const double xn = MU_IR * t + w;  // :29
       vb[ti] = valid ? xn : 0.0;
       __syncwarp();
-      const double delta = tile_row_dot<T>(aa, vb, N) - abv;  // :30
+      const double delta = tile_row_dot<R>(aa, vb, N) - abv;  // :30
       __syncwarp();
       const double res = sqrt(tile_sum<T>(valid ? delta * delta : 0.0));
       if (!irdone) {
@@ -198,9 +199,9 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
     if (valid) {
       double* out = p.grad_P + (prob * N + ti) * N;
       const double ndl = -dl;
-      if (N == T && (reinterpret_cast<uintptr_t>(p.grad_P) & 31u) == 0) {
+      if (N == R && (reinterpret_cast<uintptr_t>(p.grad_P) & 31u) == 0) {
 #pragma unroll
-        for (int j = 0; j < T; j += 4) {
+        for (int j = 0; j < R; j += 4) {
           const double2 x01 = *reinterpret_cast<const double2*>(xb + j);
           const double2 x23 = *reinterpret_cast<const double2*>(xb + j + 2);
           asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(out + j), "d"(ndl * x01.x), "d"(ndl * x01.y),
@@ -214,13 +215,13 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
   }
 }
 
-template <int T>
+template <int T, int R = T>
 static cudaError_t launch_qp_bwd_t(const BwdParams& p, cudaStream_t stream) {
   static_assert(BwdQpCfg<T>::bytes <= 48 * 1024, "backward scratch must fit the default dynamic shared memory limit");
   constexpr int WARPS = BwdQpCfg<T>::WARPS;
   const long long grid = (p.n_groups + WARPS - 1) / WARPS;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  qp_bwd_kernel<T><<<(unsigned)grid, WARPS * 32, BwdQpCfg<T>::bytes, stream>>>(p);
+  qp_bwd_kernel<T, R><<<(unsigned)grid, WARPS * 32, BwdQpCfg<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -228,7 +229,7 @@ cudaError_t launch_qp_bwd(const BwdParams& p, int T, cudaStream_t stream) {
   switch (T) {
     case 8: return launch_qp_bwd_t<8>(p, stream);
     case 16: return launch_qp_bwd_t<16>(p, stream);
-    default: return launch_qp_bwd_t<32>(p, stream);
+    default: return p.N <= 24 ? launch_qp_bwd_t<32, 24>(p, stream) : launch_qp_bwd_t<32>(p, stream);
   }
 }
 
