@@ -487,8 +487,12 @@ struct DiagRec {  // one problem's record in shared memory, in doubles
   static constexpr size_t bytes = (size_t)DIAG_CAP * D * sizeof(double) + DIAG_CAP * 8 + 16;
 };
 
+// Resident warps per SM the register budget is sized for.  28 (72 registers) and 32 (64 registers) run the diagonal
+// loop equally fast (68.8 vs 69.0 us per overlapped launch, B = 65536); at 72 registers the generic group routine inlined
+// for dense batches keeps its state in registers too (dense N = 8 QP: 313 vs 339 us), and an isolated launch is a little
+// shorter (147 vs 153 us).  Fewer warps are slower (24: 82 us, 16: 89 us).
 #ifndef DQ_DIAG_WPS
-#define DQ_DIAG_WPS 32  // resident warps per SM the QP variant's register budget is sized for
+#define DQ_DIAG_WPS 28
 #endif
 template <int PROX>
 __global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIAG_WPS : 28) / DIAG_WARPS)

@@ -1,6 +1,7 @@
 #!/bin/bash
 tag=${1:-v2}
 mkdir -p gpurun_out
-for v in "" scripts/variants/lib_f16w24.so scripts/variants/lib_f16w32.so; do
-DQ_LIB_PATH=$v python bench.py --workload qcqp_n16 --batch 65536 --steps 20 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('[$v]', d['config']['name'], d['ms_per_step'], d['roofline']['kernel_ms'])" | tee -a gpurun_out/${tag}_bench.txt
+for v in "" scripts/variants/lib_wps28.so; do
+  echo "== [$v]" | tee -a gpurun_out/${tag}_ab.txt
+  DQ_LIB_PATH=$v timeout 300 python scripts/fwd_ab.py qp_diag qp_dense 2>&1 | grep persistent | tee -a gpurun_out/${tag}_ab.txt
 done
