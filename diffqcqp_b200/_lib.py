@@ -80,3 +80,11 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().dq_launch_count())
+
+
+def set_forward_path(path: int) -> int:
+    """Forward kernel selection (process-wide): 0 = automatic (the QP / Box QP with N == 8 on the persistent-CTA kernel),
+    1 = generic kernel only (e.g. for batches known to have dense P at N == 8), 2 = persistent kernel wherever it applies.
+    Returns the previous setting.  Results do not depend on it (bit-identical on all-diagonal / all-dense batches)."""
+    return int(load().dq_set_forward_path(int(path)))
+
