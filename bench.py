@@ -327,6 +327,9 @@ def run_b200_arm(args):
     nc = N // 2
     L = _lib.load()
     fb, bb = alg_bytes(kind, N)
+    handoff = kind == "qp"  # QPFn2's forward hands diag(P) to its backward (dq_qp_*_ex): P is not re-read by the backward
+    if handoff:             # ... so the compulsory traffic is: forward +8N (the hand-off), backward 8(N^2 + 5N) instead of 8(2N^2 + 4N)
+        fb, bb = fb + 8 * N, 8 * (N * N + 5 * N)
     # one set = inputs (P, q, grad_l [, l_n, mu]) + outputs (x, grad_P, grad_q [, grad_l_n, grad_mu])
     in_bytes_per_set = 8 * B * (2 * N * N + 4 * N + (4 * nc if kind == "qcqp" else 0))
     R = max(2, int(-(-200e6 // in_bytes_per_set)) + 1)  # rotating sets: total footprint > 126 MB L2
@@ -339,6 +342,7 @@ def run_b200_arm(args):
             host0 = inp
         d = {k: v.to(dev) for k, v in inp.items()}
         d["x"] = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
+        d["st"] = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
         d["gP"] = torch.empty((B, N, N), dtype=torch.float64, device=dev)
         d["gq"] = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
         if kind == "qcqp":
@@ -350,8 +354,8 @@ def run_b200_arm(args):
 
     def fwd(d):
         if kind == "qp":
-            rc = L.dq_qp_forward(d["P"].data_ptr(), d["q"].data_ptr(), None, d["x"].data_ptr(), None, B, N, EPS,
-                                 MU_PROX, MAX_ITER, 1, sp)
+            rc = L.dq_qp_forward_ex(d["P"].data_ptr(), d["q"].data_ptr(), None, d["x"].data_ptr(), None,
+                                    d["st"].data_ptr(), B, N, EPS, MU_PROX, MAX_ITER, 1, sp)
         else:
             rc = L.dq_qcqp_forward(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(),
                                    None, d["x"].data_ptr(), None, B, N, EPS, MU_PROX, MAX_ITER, 1, sp)
@@ -359,8 +363,8 @@ def run_b200_arm(args):
 
     def bwd(d):
         if kind == "qp":
-            rc = L.dq_qp_backward(d["P"].data_ptr(), d["q"].data_ptr(), d["x"].data_ptr(), d["g"].data_ptr(),
-                                  d["gP"].data_ptr(), d["gq"].data_ptr(), B, N, sp)
+            rc = L.dq_qp_backward_ex(d["P"].data_ptr(), d["q"].data_ptr(), d["x"].data_ptr(), d["g"].data_ptr(),
+                                     d["st"].data_ptr(), d["gP"].data_ptr(), d["gq"].data_ptr(), B, N, sp)
         else:
             rc = L.dq_qcqp_backward(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(),
                                     d["x"].data_ptr(), d["g"].data_ptr(), d["gP"].data_ptr(), d["gq"].data_ptr(),
@@ -563,6 +567,7 @@ def run_b200_arm(args):
             "config": {"workload": desc, "name": args.workload, "B_per_gpu": B, "N": N, "eps": EPS,
                        "max_iter": MAX_ITER, "sharding": f"batch-sharded x{world}, no data-path collective",
                        "streams": S, "single_stream_ms_per_step": serial_ms_per_step,
+                       "fwd_bwd_handoff": handoff,
                        "l2_policy": f"{R} rotating input sets, {R * in_bytes_per_set / 1e6:.0f} MB footprint > 126 MB L2"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -17,7 +17,7 @@ SYMBOLS = [
     "dq_version", "dq_build_arch", "dq_error_string", "dq_last_cuda_error", "dq_max_n",
     "dq_qp_forward", "dq_qp_backward", "dq_qcqp_forward", "dq_qcqp_backward",
     "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release", "dq_qcqp_backward_ex", "dq_boxqp_forward", "dq_boxqp_backward",
-    "dq_set_forward_path",
+    "dq_set_forward_path", "dq_qp_forward_ex", "dq_qp_backward_ex",
 ]
 
 _vp = ctypes.c_void_p
@@ -52,6 +52,10 @@ def load():
     L.dq_qp_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _f64, _i32, _i32, _vp]
     L.dq_qp_backward.restype = ctypes.c_int
     L.dq_qp_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]
+    L.dq_qp_forward_ex.restype = ctypes.c_int
+    L.dq_qp_forward_ex.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _f64, _i32, _i32, _vp]
+    L.dq_qp_backward_ex.restype = ctypes.c_int
+    L.dq_qp_backward_ex.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]
     L.dq_qcqp_forward.restype = ctypes.c_int
     L.dq_qcqp_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _f64, _i32, _i32, _vp]
     L.dq_qcqp_backward.restype = ctypes.c_int

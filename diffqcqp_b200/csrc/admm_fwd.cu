@@ -369,6 +369,8 @@ __device__ __forceinline__ void solve_group(const FwdParams& p, long long first,
     else nz |= (prow[j] != 0.0);
   }
   const bool dense = __any_sync(FULL_MASK, nz);  // warp-uniform: the whole group takes one path
+  // hand-off to the backward: the diagonal of a problem solved on the diagonal path, NaN otherwise
+  if (p.state != nullptr && t.valid) p.state[prob * N + ti] = dense ? __longlong_as_double(0x7ff8000000000000LL) : t.pdiag;
 
   int cur = 0;  // gemv double buffer: one __syncwarp per product (writes of step k+2 are fenced by step k+1's)
   if (dense) {  // zero the padded scratch once; entries with an index >= N are never written afterwards
@@ -583,6 +585,7 @@ __global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIA
       if (valid) {
         const long long e = (b0 + w0 + j) * 8 + ti;
         rec[R::Q + ti] = __ldg(p.q + e);
+        if (p.state != nullptr) p.state[e] = pd;  // hand-off to the backward (this batch is diagonal)
         if (QCQP) {  // mul_n = l_n o mu   pybindings.cpp:57
           const long long c = (b0 + w0 + j) * 4 + (ti >> 1);
           rec[R::X0 + ti] = __dmul_rn(__ldg(p.l_n + c), __ldg(p.mu + c));

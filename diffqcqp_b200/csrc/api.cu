@@ -39,8 +39,9 @@ int check_common(const void* P, const void* q, const void* x, long long B, int N
 int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n, const double* mu, double* x,
                  int32_t* iters, long long B, int N, double eps, double mu_prox, int max_iter, int adaptive,
                  cudaStream_t stream, const double* l_min = nullptr, const double* l_max = nullptr,
-                 const double* v = nullptr, const double* warm_start = nullptr) {
+                 const double* v = nullptr, const double* warm_start = nullptr, double* state = nullptr) {
   int rc = check_common(P, q, x, B, N);
+  if (!aligned8(state)) return DQ_ERR_ALIGN;
   if (rc != DQ_OK) return rc;
   const bool warm = (adaptive & DQ_FLAG_WARM_START) != 0;  // extension: off unless the caller sets the flag bit
   if (warm && B > 0 && !warm_start) return DQ_ERR_BAD_ARG;
@@ -57,6 +58,7 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
   p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.iters = iters;
   p.lo = l_min; p.hi = l_max; p.vsign = v;
   p.warm = warm ? warm_start : nullptr;
+  p.state = state;
   p.B = B; p.N = N; p.eps = eps; p.mu_prox = mu_prox; p.max_iter = max_iter;
   p.adaptive = (adaptive & DQ_FLAG_ADAPTIVE_RHO) ? 1 : 0;
   p.n_groups = (B + G - 1) / G;
@@ -70,7 +72,7 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
 int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n, const double* mu,
                   const double* x, const double* grad_x, double* grad_P, double* grad_q, double* grad_l_n,
                   double* grad_mu, long long B, int N, cudaStream_t stream, double* gamma = nullptr,
-                  double* dgamma = nullptr) {
+                  double* dgamma = nullptr, const double* state = nullptr) {
   int rc = check_common(P, q, x, B, N);
   if (rc != DQ_OK) return rc;
   if (B > 0 && !grad_x) return DQ_ERR_BAD_ARG;
@@ -88,6 +90,7 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
   p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.grad_x = grad_x;
   p.grad_P = grad_P; p.grad_q = grad_q; p.grad_l_n = grad_l_n; p.grad_mu = grad_mu;
   p.gamma = gamma; p.dgamma = dgamma;
+  p.state = (!qcqp && aligned8(state)) ? state : nullptr;
   p.B = B; p.N = N;
   p.n_groups = (B + G - 1) / G;
   cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, stream) : dq::launch_qp_bwd(p, T, stream);
@@ -383,6 +386,19 @@ int dq_qp_backward(const double* P, const double* q, const double* x, const doub
                    double* grad_q, int64_t B, int32_t N, void* stream) {
   return backward_impl(false, P, q, nullptr, nullptr, x, grad_x, grad_P, grad_q, nullptr, nullptr, B, N,
                        (cudaStream_t)stream);
+}
+
+int dq_qp_forward_ex(const double* P, const double* q, const double* warm_start, double* x, int32_t* iters,
+                     double* state, int64_t B, int32_t N, double eps, double mu_prox, int32_t max_iter,
+                     int32_t adaptative_rho, void* stream) {
+  return forward_impl(false, P, q, nullptr, nullptr, x, iters, B, N, eps, mu_prox, max_iter, adaptative_rho,
+                      (cudaStream_t)stream, nullptr, nullptr, nullptr, warm_start, state);
+}
+
+int dq_qp_backward_ex(const double* P, const double* q, const double* x, const double* grad_x, const double* state,
+                      double* grad_P, double* grad_q, int64_t B, int32_t N, void* stream) {
+  return backward_impl(false, P, q, nullptr, nullptr, x, grad_x, grad_P, grad_q, nullptr, nullptr, B, N,
+                       (cudaStream_t)stream, nullptr, nullptr, state);
 }
 
 int dq_qcqp_forward(const double* P, const double* q, const double* l_n, const double* mu,

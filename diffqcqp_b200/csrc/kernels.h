@@ -15,6 +15,7 @@ struct FwdParams {
   const double* hi;     // Box / SignedBox QP only: l_max
   const double* vsign;  // SignedBox QP only: v
   const double* warm;   // NULL (the reference's behaviour: warm_start is dead) or the (B,N) start of l_2 (DQ_FLAG_WARM_START)
+  double* state;        // nullable (B,N): forward -> backward hand-off: diag(P) of a diagonal problem, NaN for a dense one
   double* x;
   int32_t* iters;  // nullable
   long long B;
@@ -39,6 +40,7 @@ struct BwdParams {
   double* grad_mu;   // nullable, QCQP only
   double* gamma;     // nullable, QCQP only: the duals of dualFromPrimalQCQP (B, N/2)
   double* dgamma;    // nullable, QCQP only: blgamma[:nc] of solveDerivativesQCQP (B, N/2)
+  const double* state;  // nullable, QP only: the forward's hand-off (see FwdParams::state); lets diagonal groups skip P
   long long B;
   int N;
   long long n_groups;  // ceil(B / (32/T)): one warp per group

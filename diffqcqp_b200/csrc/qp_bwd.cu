@@ -74,21 +74,32 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
   double* db = wsm + 64 * T + 32 + tile_base;  // [T] reciprocal pivots
   double* xb = wsm + 64 * T + 64 + tile_base;  // [T] x broadcast for the outer product
 
-  // ---- inputs straight into registers
+  // ---- inputs straight into registers.  When the forward handed over diag(P) (p.state: a number for a problem it
+  // found diagonal, NaN otherwise) and every problem of this group is diagonal, P is not read at all: 8N^2 of the
+  // 8(2N^2 + 4N) bytes this kernel otherwise moves per problem.
   const bool vecP = (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0;
-  double prow[R];
-  load_row_bwd<R>(prow, p.P + (prob * N + ti) * N, N, valid, vecP);
   const double qi = valid ? __ldg(p.q + prob * N + ti) : 0.0;
   const double xi = valid ? __ldg(p.x + prob * N + ti) : 0.0;
   const double gi = valid ? __ldg(p.grad_x + prob * N + ti) : 0.0;
+  const double sv = (p.state != nullptr && valid) ? __ldg(p.state + prob * N + ti) : 0.0;
+  const bool stashed = p.state != nullptr && !__any_sync(FULL_MASK, sv != sv);  // warp-uniform
+  double prow[R];
   double pdiag = 1.0;
-  bool nz = false;
+  bool dense = false;
+  if (stashed) {
+    pdiag = valid ? sv : 1.0;
 #pragma unroll
-  for (int j = 0; j < R; j++) {
-    if (j == ti) pdiag = valid ? prow[j] : 1.0;
-    else nz |= (prow[j] != 0.0);
+    for (int j = 0; j < R; j++) prow[j] = 0.0;  // only the dense branch reads it
+  } else {
+    load_row_bwd<R>(prow, p.P + (prob * N + ti) * N, N, valid, vecP);
+    bool nz = false;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      if (j == ti) pdiag = valid ? prow[j] : 1.0;
+      else nz |= (prow[j] != 0.0);
+    }
+    dense = __any_sync(FULL_MASK, nz);  // warp-uniform
   }
-  const bool dense = __any_sync(FULL_MASK, nz);  // warp-uniform
 
   double dl;  // this lane's entry of bl
   if (!dense) {

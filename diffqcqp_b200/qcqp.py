@@ -117,7 +117,7 @@ def _check_shapes(P, q, l_n=None, mu=None):
 
 
 # --------------------------------------------------------------------------- raw batched ops
-def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None):
+def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None, state=None):
     """Batched solveQP on CUDA tensors: P (B,N,N), q (B,N,1) -> x (B,N,1) [, iters (B,) int32].
     warm_start (B,N,1), when given, is where the iteration starts (extension; None = the reference's behaviour)."""
     dev = P.device
@@ -126,13 +126,14 @@ def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_it
     iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
     L = _lib.load()
     with torch.cuda.device(dev):
-        rc = L.dq_qp_forward(_ptr(P), _ptr(q), _ptr(warm_start), _ptr(x), _ptr(iters), B, N, float(eps), float(mu_prox),
-                             int(max_iter), _flags(adaptative_rho, warm_start), _stream_ptr(dev))
+        # state: optional (B,N,1) buffer the forward fills for the backward (diag(P) of diagonal problems, NaN otherwise)
+        rc = L.dq_qp_forward_ex(_ptr(P), _ptr(q), _ptr(warm_start), _ptr(x), _ptr(iters), _ptr(state), B, N, float(eps),
+                                float(mu_prox), int(max_iter), _flags(adaptative_rho, warm_start), _stream_ptr(dev))
     _lib.check(rc, "dq_qp_forward")
     return (x, iters) if return_iters else x
 
 
-def qp_backward(P, q, x, grad_x, need_P=True, need_q=True):
+def qp_backward(P, q, x, grad_x, need_P=True, need_q=True, state=None):
     dev = P.device
     B, N = P.size(0), P.size(1)
     gP = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need_P else None
@@ -140,8 +141,8 @@ def qp_backward(P, q, x, grad_x, need_P=True, need_q=True):
     if need_P or need_q:
         L = _lib.load()
         with torch.cuda.device(dev):
-            rc = L.dq_qp_backward(_ptr(P), _ptr(q), _ptr(x), _ptr(grad_x), _ptr(gP), _ptr(gq), B, N,
-                                  _stream_ptr(dev))
+            rc = L.dq_qp_backward_ex(_ptr(P), _ptr(q), _ptr(x), _ptr(grad_x), _ptr(state), _ptr(gP), _ptr(gq), B, N,
+                                     _stream_ptr(dev))
         _lib.check(rc, "dq_qp_backward")
     return gP, gq
 
@@ -222,7 +223,10 @@ class QPFn2(Function):
         _check_shapes(P, q)
         dev = _compute_device(P, q)
         Pd, qd = _as_dev(P, dev, "P"), _as_dev(q, dev, "q")
-        x = qp_forward(Pd, qd, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q))
+        # forward -> backward hand-off: diag(P) of the problems solved on the diagonal path (the backward then skips P)
+        state = torch.empty_like(qd) if any(ctx.needs_input_grad[:2]) else None
+        x = qp_forward(Pd, qd, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q), state=state)
+        ctx.state = state
         ctx.save_for_backward(Pd, qd, x)
         ctx.out_device = q.device
         return _back_to(x, q.device)
@@ -231,7 +235,7 @@ class QPFn2(Function):
     def backward(ctx, grad_l):
         Pd, qd, x = ctx.saved_tensors
         g = _as_dev(grad_l, Pd.device, "grad_l")
-        gP, gq = qp_backward(Pd, qd, x, g, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        gP, gq = qp_backward(Pd, qd, x, g, ctx.needs_input_grad[0], ctx.needs_input_grad[1], state=ctx.state)
         return _back_to(gP, ctx.out_device), _back_to(gq, ctx.out_device), None, None, None, None
 
 

@@ -79,6 +79,20 @@ int dq_qp_backward(const double* P, const double* q, const double* x, const doub
                    double* grad_P, double* grad_q, int64_t B, int32_t N, void* stream);
 
 /*
+ * The same pair with a forward -> backward hand-off: `state` is a caller-allocated (B,N)
+ * buffer.  The forward writes diag(P) of every problem it solved on its diagonal path (NaN for the others); given
+ * the same buffer, the backward does not read P for groups of diagonal problems -- 8N^2 of its 8(2N^2 + 4N) bytes
+ * per problem.  P, q, x must be the tensors the forward saw (what torch.autograd saves).  Results are identical to
+ * dq_qp_forward / dq_qp_backward; state == NULL makes them the same calls.
+ */
+int dq_qp_forward_ex(const double* P, const double* q, const double* warm_start, double* x,
+                     int32_t* iters, double* state, int64_t B, int32_t N, double eps, double mu_prox,
+                     int32_t max_iter, int32_t adaptative_rho, void* stream);
+int dq_qp_backward_ex(const double* P, const double* q, const double* x, const double* grad_x,
+                      const double* state, double* grad_P, double* grad_q, int64_t B, int32_t N,
+                      void* stream);
+
+/*
  * Forward ADMM solve of   min 1/2 x'Px + q'x  s.t. |(x_2i, x_2i+1)| <= l_n[i]*mu[i]
  * (pybindings.cpp:54-60, Solver.cpp:505-582).  N must be even; l_n, mu are (B, N/2).
  */

@@ -804,3 +804,43 @@ def test_warm_start_extension_qcqp_and_box(dq, wl, oracle):
     xb2, itb2 = dq.boxqp_forward(*dev(Pd, qd, lo, hi), EPS, 1000, return_iters=True, warm_start=xb)
     assert float(itb2.double().mean()) <= 3.0 < float(itb.double().mean())
     assert float((xb2 - xb).abs().max()) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------ forward -> backward hand-off
+def test_forward_backward_handoff(dq, wl, cuda_lib):
+    """dq_qp_forward_ex / dq_qp_backward_ex: the forward hands diag(P) of the problems it solved on its diagonal path to
+    the backward, which then does not read P for them.  Gradients are bit-identical with and without the hand-off, on
+    both forward kernels, for diagonal, dense and mixed batches and for N that does not fill its tile."""
+    for N, B in ((8, 5003), (8, 17), (5, 333), (16, 515), (24, 130), (32, 65)):
+        P, q, g = wl.qp_diag(B, N, seed=800 + N)
+        Pd_, _, _ = wl.qp_dense(B, N, seed=801 + N)
+        Pm = P.clone()
+        Pm[3:B:7] = Pd_[3:B:7]
+        for name, PP in (("diag", P), ("dense", Pd_), ("mixed", Pm)):
+            Pc, qc, gc = dev(PP, q, g)
+            for path in (0, 1):
+                try:
+                    cuda_lib.dq_set_forward_path(path)
+                    st = torch.full((B, N, 1), 7.0, dtype=torch.float64, device="cuda")
+                    x = dq.qp_forward(Pc, qc, EPS, 1000, state=st)
+                finally:
+                    cuda_lib.dq_set_forward_path(0)
+                gP0, gq0 = dq.qp_backward(Pc, qc, x, gc)
+                gP1, gq1 = dq.qp_backward(Pc, qc, x, gc, state=st)
+                assert torch.equal(gP0.view(torch.int64), gP1.view(torch.int64)), (N, name, path)
+                assert torch.equal(gq0.view(torch.int64), gq1.view(torch.int64)), (N, name, path)
+                diag = torch.diagonal(Pc, dim1=1, dim2=2).unsqueeze(-1)
+                isn = torch.isnan(st)
+                assert torch.equal(st[~isn], diag[~isn]), (N, name, path)       # what is handed over is diag(P) ...
+                if name == "diag":
+                    assert not bool(isn.any()), (N, name, path)                  # ... for every diagonal problem
+                if name == "dense":
+                    assert bool(isn.all()), (N, name, path)
+    # the layer uses it: same gradients as the raw ops without it
+    import qcqp as ref_surface
+    P, q, g = wl.qp_diag(2049, 8, seed=850)
+    Pc, qc = P.cuda().requires_grad_(True), q.cuda().requires_grad_(True)
+    x = ref_surface.QPFn2.apply(Pc, qc, torch.zeros_like(qc), EPS, 1000)
+    (x * g.cuda()).sum().backward()
+    gP0, gq0 = dq.qp_backward(P.cuda(), q.cuda(), x.detach(), g.cuda())
+    assert torch.equal(Pc.grad, gP0) and torch.equal(qc.grad, gq0)
