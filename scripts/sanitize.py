@@ -47,3 +47,11 @@ run("warm start qp dense N=8", lambda: dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 2
 P, q, g = wl.qp_diag(33, 8, seed=6)
 x0 = dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 200)
 run("warm start qp diag N=8", lambda: dq.qp_forward(P.cuda(), q.cuda(), 1e-7, 200, warm_start=x0))
+
+# forward -> backward hand-off (dq_qp_forward_ex / dq_qp_backward_ex) on both forward kernels, diagonal and mixed batches
+for path in (0, 1):
+    L.dq_set_forward_path(path)
+    for PP, tag in ((Pd, "diag"), (Pm, "mixed")):
+        st = torch.empty(300, 8, 1, dtype=torch.float64, device="cuda")
+        run(f"hand-off {tag} path={path}", lambda: dq.qp_backward(PP, qd, dq.qp_forward(PP, qd, 1e-7, 300, state=st), torch.ones_like(qd), state=st))
+L.dq_set_forward_path(0)
