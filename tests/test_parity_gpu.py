@@ -844,3 +844,25 @@ def test_forward_backward_handoff(dq, wl, cuda_lib):
     (x * g.cuda()).sum().backward()
     gP0, gq0 = dq.qp_backward(P.cuda(), q.cuda(), x.detach(), g.cuda())
     assert torch.equal(Pc.grad, gP0) and torch.equal(qc.grad, gq0)
+
+
+def test_cuda_graph_capture_and_replay(dq, wl):
+    """The entry points only enqueue work on the caller's stream (no host sync, no allocation after the first call), so
+    a forward + backward pair can be captured in a CUDA graph and replayed: same bits as the eager calls, on both the
+    persistent (N = 8) and the generic (N = 16) forward."""
+    for gen, B, N in (("qp_diag", 4099, 8), ("qp_dense", 515, 16)):
+        P, q, g = getattr(wl, gen)(B, N, seed=900 + N)
+        Pd, qd, gd = dev(P, q, g)
+        st = torch.empty_like(qd)
+        x_ref = dq.qp_forward(Pd, qd, EPS, 1000, state=st)          # also the warm-up (first-call attribute queries)
+        gP_ref, gq_ref = dq.qp_backward(Pd, qd, x_ref, gd, state=st)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            x = dq.qp_forward(Pd, qd, EPS, 1000, state=st)
+            gP, gq = dq.qp_backward(Pd, qd, x, gd, state=st)
+        for _ in range(3):
+            x.zero_(); gP.zero_(); gq.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(x, x_ref) and torch.equal(gP, gP_ref) and torch.equal(gq, gq_ref)
