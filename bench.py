@@ -327,9 +327,11 @@ def run_b200_arm(args):
     nc = N // 2
     L = _lib.load()
     fb, bb = alg_bytes(kind, N)
-    handoff = kind == "qp"  # QPFn2's forward hands diag(P) to its backward (dq_qp_*_ex): P is not re-read by the backward
-    if handoff:             # ... so the compulsory traffic is: forward +8N (the hand-off), backward 8(N^2 + 5N) instead of 8(2N^2 + 4N)
-        fb, bb = fb + 8 * N, 8 * (N * N + 5 * N)
+    # QPFn2 / QCQPFn2 hand diag(P) from the forward to the backward (dq_*_forward_ex / dq_*_backward_ex*): for a diagonal
+    # P the backward does not re-read it, so the compulsory traffic is forward +8N (the hand-off) and backward -8N^2 +8N
+    handoff = kw["gen"] in ("qp_diag", "qcqp_diag")
+    if handoff:
+        fb, bb = fb + 8 * N, bb - 8 * N * N + 8 * N
     # one set = inputs (P, q, grad_l [, l_n, mu]) + outputs (x, grad_P, grad_q [, grad_l_n, grad_mu])
     in_bytes_per_set = 8 * B * (2 * N * N + 4 * N + (4 * nc if kind == "qcqp" else 0))
     R = max(2, int(-(-200e6 // in_bytes_per_set)) + 1)  # rotating sets: total footprint > 126 MB L2
@@ -357,8 +359,8 @@ def run_b200_arm(args):
             rc = L.dq_qp_forward_ex(d["P"].data_ptr(), d["q"].data_ptr(), None, d["x"].data_ptr(), None,
                                     d["st"].data_ptr(), B, N, EPS, MU_PROX, MAX_ITER, 1, sp)
         else:
-            rc = L.dq_qcqp_forward(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(),
-                                   None, d["x"].data_ptr(), None, B, N, EPS, MU_PROX, MAX_ITER, 1, sp)
+            rc = L.dq_qcqp_forward_ex(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(),
+                                      None, d["x"].data_ptr(), None, d["st"].data_ptr(), B, N, EPS, MU_PROX, MAX_ITER, 1, sp)
         _lib.check(rc, "forward")
 
     def bwd(d):
@@ -366,9 +368,9 @@ def run_b200_arm(args):
             rc = L.dq_qp_backward_ex(d["P"].data_ptr(), d["q"].data_ptr(), d["x"].data_ptr(), d["g"].data_ptr(),
                                      d["st"].data_ptr(), d["gP"].data_ptr(), d["gq"].data_ptr(), B, N, sp)
         else:
-            rc = L.dq_qcqp_backward(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(),
-                                    d["x"].data_ptr(), d["g"].data_ptr(), d["gP"].data_ptr(), d["gq"].data_ptr(),
-                                    d["gl"].data_ptr(), d["gm"].data_ptr(), B, N, sp)
+            rc = L.dq_qcqp_backward_ex2(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(),
+                                        d["x"].data_ptr(), d["g"].data_ptr(), d["st"].data_ptr(), d["gP"].data_ptr(),
+                                        d["gq"].data_ptr(), d["gl"].data_ptr(), d["gm"].data_ptr(), None, None, B, N, sp)
         _lib.check(rc, "backward")
 
     def barrier():

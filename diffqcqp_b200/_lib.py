@@ -18,6 +18,7 @@ SYMBOLS = [
     "dq_qp_forward", "dq_qp_backward", "dq_qcqp_forward", "dq_qcqp_backward",
     "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release", "dq_qcqp_backward_ex", "dq_boxqp_forward", "dq_boxqp_backward",
     "dq_set_forward_path", "dq_qp_forward_ex", "dq_qp_backward_ex",
+    "dq_qcqp_forward_ex", "dq_qcqp_backward_ex2",
 ]
 
 _vp = ctypes.c_void_p
@@ -66,6 +67,10 @@ def load():
     L.dq_boxqp_backward.argtypes = [_vp] * 10 + [_i64, _i32, _vp]
     L.dq_qcqp_backward_ex.restype = ctypes.c_int
     L.dq_qcqp_backward_ex.argtypes = [_vp] * 12 + [_i64, _i32, _vp]
+    L.dq_qcqp_forward_ex.restype = ctypes.c_int
+    L.dq_qcqp_forward_ex.argtypes = [_vp] * 8 + [_i64, _i32, _f64, _f64, _i32, _i32, _vp]
+    L.dq_qcqp_backward_ex2.restype = ctypes.c_int
+    L.dq_qcqp_backward_ex2.argtypes = [_vp] * 13 + [_i64, _i32, _vp]
     L.dq_qp_solve_host.restype = ctypes.c_int
     L.dq_qp_solve_host.argtypes = [_vp] * 6 + [_i64, _i32, _f64, _f64, _i32, _i32]
     L.dq_qcqp_solve_host.restype = ctypes.c_int

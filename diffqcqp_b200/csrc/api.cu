@@ -90,7 +90,7 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
   p.P = P; p.q = q; p.l_n = l_n; p.mu = mu; p.x = x; p.grad_x = grad_x;
   p.grad_P = grad_P; p.grad_q = grad_q; p.grad_l_n = grad_l_n; p.grad_mu = grad_mu;
   p.gamma = gamma; p.dgamma = dgamma;
-  p.state = (!qcqp && aligned8(state)) ? state : nullptr;
+  p.state = aligned8(state) ? state : nullptr;
   p.B = B; p.N = N;
   p.n_groups = (B + G - 1) / G;
   cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, stream) : dq::launch_qp_bwd(p, T, stream);
@@ -455,6 +455,21 @@ int dq_qcqp_backward_ex(const double* P, const double* q, const double* l_n, con
   if (!aligned8(gamma) || !aligned8(dgamma)) return DQ_ERR_ALIGN;
   return backward_impl(true, P, q, l_n, mu, x, grad_x, grad_P, grad_q, grad_l_n, grad_mu, B, N, (cudaStream_t)stream,
                        gamma, dgamma);
+}
+
+int dq_qcqp_forward_ex(const double* P, const double* q, const double* l_n, const double* mu, const double* warm_start,
+                       double* x, int32_t* iters, double* state, int64_t B, int32_t N, double eps, double mu_prox,
+                       int32_t max_iter, int32_t adaptative_rho, void* stream) {
+  return forward_impl(true, P, q, l_n, mu, x, iters, B, N, eps, mu_prox, max_iter, adaptative_rho,
+                      (cudaStream_t)stream, nullptr, nullptr, nullptr, warm_start, state);
+}
+
+int dq_qcqp_backward_ex2(const double* P, const double* q, const double* l_n, const double* mu, const double* x,
+                         const double* grad_x, const double* state, double* grad_P, double* grad_q, double* grad_l_n,
+                         double* grad_mu, double* gamma, double* dgamma, int64_t B, int32_t N, void* stream) {
+  if (!aligned8(gamma) || !aligned8(dgamma)) return DQ_ERR_ALIGN;
+  return backward_impl(true, P, q, l_n, mu, x, grad_x, grad_P, grad_q, grad_l_n, grad_mu, B, N, (cudaStream_t)stream,
+                       gamma, dgamma, state);
 }
 
 int dq_qp_solve_host(const double* P, const double* q, double* x, const double* grad_x, double* grad_P,

@@ -40,7 +40,7 @@ struct BwdParams {
   double* grad_mu;   // nullable, QCQP only
   double* gamma;     // nullable, QCQP only: the duals of dualFromPrimalQCQP (B, N/2)
   double* dgamma;    // nullable, QCQP only: blgamma[:nc] of solveDerivativesQCQP (B, N/2)
-  const double* state;  // nullable, QP only: the forward's hand-off (see FwdParams::state); lets diagonal groups skip P
+  const double* state;  // nullable: the forward's hand-off (see FwdParams::state); lets groups of diagonal problems skip P
   long long B;
   int N;
   long long n_groups;  // ceil(B / (32/T)): one warp per group

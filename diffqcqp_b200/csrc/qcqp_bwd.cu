@@ -94,11 +94,19 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     const double rc = lnc * muc;  // mul_n  pybindings.cpp:66
 
     double drow[R];  // row ti of P, then of D = P + blkdiag(2 gamma_c I2)
+    // forward -> backward hand-off (p.state: diag(P) of a problem the forward found diagonal, NaN otherwise): when every
+    // problem of the group is diagonal the row is rebuilt from it and P is not read
+    const double sv = (p.state != nullptr && valid) ? __ldg(p.state + prob * N + ti) : 0.0;
+    const bool stashed = p.state != nullptr && !__any_sync(FULL_MASK, sv != sv);  // warp-uniform
     {
       const double* src = p.P + (prob * N + ti) * N;
 #pragma unroll
       for (int j = 0; j < R; j++) drow[j] = 0.0;
-      if (valid) {
+      if (stashed) {
+#pragma unroll
+        for (int j = 0; j < R; j++)
+          if (j == ti && valid) drow[j] = sv;
+      } else if (valid) {
         if (N == R && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0) {
 #pragma unroll
           for (int j = 0; j < R; j += 4)

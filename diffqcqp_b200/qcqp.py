@@ -147,21 +147,22 @@ def qp_backward(P, q, x, grad_x, need_P=True, need_q=True, state=None):
     return gP, gq
 
 
-def qcqp_forward(P, q, l_n, mu, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None):
+def qcqp_forward(P, q, l_n, mu, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None,
+                 state=None):
     dev = P.device
     B, N = P.size(0), P.size(1)
     x = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
     iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
     L = _lib.load()
     with torch.cuda.device(dev):
-        rc = L.dq_qcqp_forward(_ptr(P), _ptr(q), _ptr(l_n), _ptr(mu), _ptr(warm_start), _ptr(x), _ptr(iters), B, N,
-                               float(eps), float(mu_prox), int(max_iter), _flags(adaptative_rho, warm_start),
-                               _stream_ptr(dev))
+        rc = L.dq_qcqp_forward_ex(_ptr(P), _ptr(q), _ptr(l_n), _ptr(mu), _ptr(warm_start), _ptr(x), _ptr(iters),
+                                  _ptr(state), B, N, float(eps), float(mu_prox), int(max_iter),
+                                  _flags(adaptative_rho, warm_start), _stream_ptr(dev))
     _lib.check(rc, "dq_qcqp_forward")
     return (x, iters) if return_iters else x
 
 
-def qcqp_backward(P, q, l_n, mu, x, grad_x, need=(True, True, True, True)):
+def qcqp_backward(P, q, l_n, mu, x, grad_x, need=(True, True, True, True), state=None):
     dev = P.device
     B, N = P.size(0), P.size(1)
     nc = N // 2
@@ -172,8 +173,8 @@ def qcqp_backward(P, q, l_n, mu, x, grad_x, need=(True, True, True, True)):
     if any(need):
         L = _lib.load()
         with torch.cuda.device(dev):
-            rc = L.dq_qcqp_backward(_ptr(P), _ptr(q), _ptr(l_n), _ptr(mu), _ptr(x), _ptr(grad_x), _ptr(gP),
-                                    _ptr(gq), _ptr(gl), _ptr(gm), B, N, _stream_ptr(dev))
+            rc = L.dq_qcqp_backward_ex2(_ptr(P), _ptr(q), _ptr(l_n), _ptr(mu), _ptr(x), _ptr(grad_x), _ptr(state), _ptr(gP),
+                                        _ptr(gq), _ptr(gl), _ptr(gm), None, None, B, N, _stream_ptr(dev))
         _lib.check(rc, "dq_qcqp_backward")
     return gP, gq, gl, gm
 
@@ -248,7 +249,10 @@ class QCQPFn2(Function):
         dev = _compute_device(P, q, l_n, mu)
         Pd, qd = _as_dev(P, dev, "P"), _as_dev(q, dev, "q")
         ld, md = _as_dev(l_n, dev, "l_n"), _as_dev(mu, dev, "mu")
-        x = qcqp_forward(Pd, qd, ld, md, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q))
+        state = torch.empty_like(qd) if any(ctx.needs_input_grad[:4]) else None  # forward -> backward hand-off
+        x = qcqp_forward(Pd, qd, ld, md, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q),
+                         state=state)
+        ctx.state = state
         ctx.save_for_backward(Pd, qd, ld, md, x)
         ctx.out_device = q.device
         return _back_to(x, q.device)
@@ -257,7 +261,7 @@ class QCQPFn2(Function):
     def backward(ctx, grad_l):
         Pd, qd, ld, md, x = ctx.saved_tensors
         g = _as_dev(grad_l, Pd.device, "grad_l")
-        gP, gq, gl, gm = qcqp_backward(Pd, qd, ld, md, x, g, tuple(ctx.needs_input_grad[:4]))
+        gP, gq, gl, gm = qcqp_backward(Pd, qd, ld, md, x, g, tuple(ctx.needs_input_grad[:4]), state=ctx.state)
         o = ctx.out_device
         return _back_to(gP, o), _back_to(gq, o), _back_to(gl, o), _back_to(gm, o), None, None, None, None
 

@@ -141,6 +141,20 @@ int dq_qcqp_backward_ex(const double* P, const double* q, const double* l_n, con
                         int32_t N, void* stream);
 
 /*
+ * The QCQP pair with the forward -> backward hand-off of dq_qp_forward_ex / dq_qp_backward_ex (`state` (B,N): diag(P)
+ * of the problems solved on the diagonal path, NaN otherwise; the backward then does not read P for groups of diagonal
+ * problems).  dq_qcqp_backward_ex2 is dq_qcqp_backward_ex plus `state`; gamma / dgamma may be NULL.
+ */
+int dq_qcqp_forward_ex(const double* P, const double* q, const double* l_n, const double* mu,
+                       const double* warm_start, double* x, int32_t* iters, double* state, int64_t B,
+                       int32_t N, double eps, double mu_prox, int32_t max_iter, int32_t adaptative_rho,
+                       void* stream);
+int dq_qcqp_backward_ex2(const double* P, const double* q, const double* l_n, const double* mu,
+                         const double* x, const double* grad_x, const double* state, double* grad_P,
+                         double* grad_q, double* grad_l_n, double* grad_mu, double* gamma, double* dgamma,
+                         int64_t B, int32_t N, void* stream);
+
+/*
  * Host-buffer path (what a caller holding CPU arrays, like the reference's users, calls): copies
  * the inputs host->device in chunks on three streams so that the copy of one chunk overlaps the
  * solve of another and the read-back of a third, runs forward (and, when grad_x != NULL,

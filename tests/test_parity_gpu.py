@@ -866,3 +866,31 @@ def test_cuda_graph_capture_and_replay(dq, wl):
             graph.replay()
             torch.cuda.synchronize()
             assert torch.equal(x, x_ref) and torch.equal(gP, gP_ref) and torch.equal(gq, gq_ref)
+
+
+def test_forward_backward_handoff_qcqp(dq, wl, cuda_lib):
+    """The QCQP pair with the hand-off (dq_qcqp_forward_ex / dq_qcqp_backward_ex2): gradients bit-identical with and
+    without it, diagonal / dense / mixed P, both forward kernels where both apply (N = 8)."""
+    for N, B in ((8, 4099), (8, 9), (6, 77), (16, 513), (24, 130)):
+        P, q, l_n, mu, g = wl.qcqp_diag(B, N, seed=860 + N)
+        Pd_ = wl.qcqp_dense(B, N, seed=861 + N)[0]
+        Pm = P.clone()
+        Pm[2:B:5] = Pd_[2:B:5]
+        for name, PP in (("diag", P), ("dense", Pd_), ("mixed", Pm)):
+            a = dev(PP, q, l_n, mu)
+            gc = g.cuda()
+            for path in ((0, 2) if N == 8 else (0,)):
+                try:
+                    cuda_lib.dq_set_forward_path(path)
+                    st = torch.full((B, N, 1), 7.0, dtype=torch.float64, device="cuda")
+                    x = dq.qcqp_forward(*a, EPS, 1000, state=st)
+                finally:
+                    cuda_lib.dq_set_forward_path(0)
+                g0 = dq.qcqp_backward(*a, x, gc)
+                g1 = dq.qcqp_backward(*a, x, gc, state=st)
+                for u, v in zip(g0, g1):
+                    assert torch.equal(u.view(torch.int64), v.view(torch.int64)), (N, name, path)
+                if name == "diag":
+                    assert not bool(torch.isnan(st).any())
+                if name == "dense":
+                    assert bool(torch.isnan(st).all())
