@@ -19,6 +19,8 @@
 // non-FMA x86-64 build of the reference up to the value of pow() and the association of the norms in
 // power_iteration.  Dense matrix-vector products and the Cholesky use FMAs (Eigen's own summation
 // order is packetised, so there is no bit-level target there).
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -724,12 +726,26 @@ __global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIA
     // queue and computes its first iteration into Q; a tile whose rho changed recomputes Q.  For the prox that
     // shuffles inside step (disks) the recomputation is done by the whole warp, tiles that did not change recompute
     // the same bits.
-    auto body = [&](Iter& P, Iter& Q) {
+    // SOLO: this warp's only live tile is a straggler and the queue is empty.  Nothing competes for issue slots then,
+    // the trip latency is what counts: the tile maximum is taken by two full-mask redux (idle tiles contribute zero),
+    // 65 cycles instead of 128 for the three-stage 64-bit butterfly (profiles/r01_micro_redux.txt); same value.
+    auto body = [&](Iter& P, Iter& Q, auto solo_tag) {
+      constexpr bool SOLO = decltype(solo_tag)::value;
       step(P, Q);
       ++it;
       const double adl = fabs(P.dl), pdu = fabs(P.du);
       bool stop = (__ballot_sync(FULL_MASK, __dmul_rn(rho, adl) < eps) & tmask) == tmask;  // :88 / :548
-      const double rd = __dmul_rn(rho, tile_absmax<T>(P.dl));
+      double amax;
+      if constexpr (SOLO) {
+        const unsigned hi = live ? ((unsigned)__double2hiint(P.dl) & 0x7fffffffu) : 0u;
+        const unsigned lo = live ? (unsigned)__double2loint(P.dl) : 0u;
+        const unsigned mh = __reduce_max_sync(FULL_MASK, hi);
+        const unsigned ml = __reduce_max_sync(FULL_MASK, hi == mh ? lo : 0u);
+        amax = __hiloint2double((int)mh, (int)ml);
+      } else {
+        amax = tile_absmax<T>(P.dl);
+      }
+      const double rd = __dmul_rn(rho, amax);
       if (QCQP) {
         if (__any_sync(FULL_MASK, stop && live)) {
           const double thr = __dadd_rn(eps, __dmul_rn(1e-4, sqrt(tile_sum<T>(__dmul_rn(P.l, P.l)))));
@@ -819,9 +835,18 @@ __global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIA
     A.l2 = 0.0; A.u = 0.0; A.qprox = qi; A.dl = A.du = A.l = 0.0;
     step(A, B);  // iteration 1, undecided
     while (nlive > 0) {  // ping-pong between the two register sets; nlive is warp-uniform
-      body(B, A);
+      if (nlive == 1 && ctl[0] >= nb) {  // one straggler left in this warp and nothing to refill from: the latency loop
+        while (true) {
+          body(B, A, std::true_type{});
+          if (nlive <= 0) break;
+          body(A, B, std::true_type{});
+          if (nlive <= 0) break;
+        }
+        break;
+      }
+      body(B, A, std::false_type{});
       if (nlive <= 0) break;
-      body(A, B);
+      body(A, B, std::false_type{});
     }
     __syncthreads();  // the records are rewritten by the next batch
   }
