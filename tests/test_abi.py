@@ -138,3 +138,39 @@ def test_algorithmic_bytes_match_survey():
     assert wl.qcqp_bytes(16) == 7424 - 128
     assert wl.qcqp_bytes(24) == 15744 - 192
     assert wl.qp_bytes(32) == 26368 - 256
+
+
+def test_sass_of_the_persistent_forward_hot_loop():
+    """Regression guard for the headline kernel (admm_fwd_diag8_kernel<PROX_NONNEG>): the code object holds it, it fits 72
+    registers, its ADMM loops carry no divergence guards (BRA.DIV: the warp index is read through a shuffle so that
+    the compiler knows the loop to be warp-uniform) and no local-memory traffic, and the straggler loop uses the uniform
+    redux (CREDUX) for the tile maximum."""
+    import re
+    import shutil
+    import subprocess
+    from diffqcqp_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    fun = "_ZN2dq21admm_fwd_diag8_kernelILi0EEEvNS_9FwdParamsE"
+    res = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    m = re.search(fun + r".*?\n\s*REG:(\d+)", res, re.S)
+    assert m and int(m.group(1)) <= 72, m and m.group(1)
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", fun, _lib.LIB_PATH], capture_output=True, text=True).stdout
+    ins = [(int(mm.group(1), 16), mm.group(2)) for mm in re.finditer(r"/\*([0-9a-f]{4,5})\*/\s+(.*?)\s*;", sass)]
+    assert len(ins) > 3000
+    assert any("CREDUX" in t for _, t in ins)
+    # the diagonal loops: backward branches whose body holds DSETP + VOTE and spans 400..900 instructions, ahead of the
+    # inlined generic group routine's loops (the two at the lowest addresses: normal and straggler loop)
+    loops = []
+    for a, t in ins:
+        mm = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", t)
+        if mm and int(mm.group(1), 16) < a and 400 <= (a - int(mm.group(1), 16)) // 16 <= 900:
+            loops.append((int(mm.group(1), 16), a))
+    loops.sort()
+    assert len(loops) >= 2
+    for lo, hi in loops[:2]:
+        body = [t for a, t in ins if lo <= a <= hi]
+        assert any("VOTE" in t for t in body) and any("DSETP" in t for t in body)
+        assert not any("BRA.DIV" in t for t in body), "divergence guards inside the persistent forward's loop"
+        assert not any(t.startswith(("LDL", "STL")) or " LDL" in t or " STL" in t for t in body), "spills inside the loop"
