@@ -17,7 +17,7 @@ SYMBOLS = [
     "dq_version", "dq_build_arch", "dq_error_string", "dq_last_cuda_error", "dq_max_n",
     "dq_qp_forward", "dq_qp_backward", "dq_qcqp_forward", "dq_qcqp_backward",
     "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release", "dq_qcqp_backward_ex", "dq_boxqp_forward", "dq_boxqp_backward",
-    "dq_set_forward_path", "dq_qp_forward_ex", "dq_qp_backward_ex",
+    "dq_set_forward_path", "dq_set_forward_tuning", "dq_selftest_inverse", "dq_qp_forward_ex", "dq_qp_backward_ex",
     "dq_qcqp_forward_ex", "dq_qcqp_backward_ex2",
 ]
 
@@ -49,6 +49,10 @@ def load():
     L.dq_launch_count.restype = _i64
     L.dq_set_forward_path.restype = ctypes.c_int
     L.dq_set_forward_path.argtypes = [ctypes.c_int]
+    L.dq_set_forward_tuning.restype = _i64
+    L.dq_set_forward_tuning.argtypes = [_i32, _i64]
+    L.dq_selftest_inverse.restype = ctypes.c_int
+    L.dq_selftest_inverse.argtypes = [_vp, _i64, _vp, _vp]
     L.dq_qp_forward.restype = ctypes.c_int
     L.dq_qp_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _f64, _i32, _i32, _vp]
     L.dq_qp_backward.restype = ctypes.c_int
@@ -92,8 +96,14 @@ def launch_count() -> int:
 
 
 def set_forward_path(path: int) -> int:
-    """Forward kernel selection (process-wide): 0 = automatic (the QP / Box QP with N == 8 on the persistent-CTA kernel),
-    1 = generic kernel only (e.g. for batches known to have dense P at N == 8), 2 = persistent kernel wherever it applies.
+    """Forward kernel selection (process-wide): 0 = automatic (N == 8 QP / Box QP: thread-per-problem kernel for batches of
+    >= 32768 problems, persistent-CTA tile kernel below that), 1 = generic kernel only (e.g. for batches known to have dense
+    P at N == 8), 2 = persistent tile kernel wherever it applies, 3 = thread-per-problem kernel wherever it applies.
     Returns the previous setting.  Results do not depend on it (bit-identical on all-diagonal / all-dense batches)."""
     return int(load().dq_set_forward_path(int(path)))
 
+
+def set_forward_tuning(key: int, value: int) -> int:
+    """dq_set_forward_tuning: key 0 = park threshold (iterations) of the thread-per-problem kernel, key 1 = smallest batch
+    the automatic path gives to it.  Returns the previous value."""
+    return int(load().dq_set_forward_tuning(int(key), int(value)))

@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiffqcqp_b200.so")
-SOURCES = ["admm_fwd.cu", "qp_bwd.cu", "qcqp_bwd.cu", "boxqp_bwd.cu", "api.cu"]
-HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "diffqcqp_b200.h")]
+SOURCES = ["admm_fwd.cu", "admm_fwd_tpp.cu", "qp_bwd.cu", "qcqp_bwd.cu", "boxqp_bwd.cu", "api.cu"]
+HEADERS = ["common.cuh", "kernels.h", "admm_fwd_group.cuh", os.path.join("..", "..", "include", "diffqcqp_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -19,414 +19,12 @@
 // non-FMA x86-64 build of the reference up to the value of pow() and the association of the norms in
 // power_iteration.  Dense matrix-vector products and the Cholesky use FMAs (Eigen's own summation
 // order is packetised, so there is no bit-level target there).
-#include <type_traits>
-
-#include "common.cuh"
-#include "kernels.h"
+#include "admm_fwd_group.cuh"
 
 namespace dq {
 
-#ifndef DQ_FWD_WARPS
-#define DQ_FWD_WARPS 4
-#endif
-constexpr int FWD_WARPS = DQ_FWD_WARPS;  // warps per CTA (independent; no CTA-level barrier anywhere)
+size_t fwd_smem_bytes(int T) { return fwd_smem_bytes_impl(T); }
 
-template <int T>
-struct FwdSmem {
-  // per warp: Cholesky scratch [G][T][T] = 32*T, gemv vector double-buffered 2*32, reciprocal pivots 32
-  static constexpr int per_warp_doubles = 32 * T + 3 * 32;
-  static constexpr size_t bytes = (size_t)FWD_WARPS * per_warp_doubles * sizeof(double);
-};
-
-size_t fwd_smem_bytes(int T) {
-  switch (T) {
-    case 8: return FwdSmem<8>::bytes;
-    case 16: return FwdSmem<16>::bytes;
-    default: return FwdSmem<32>::bytes;
-  }
-}
-
-// a / b given rb = RN(1/b): the correctly rounded IEEE quotient (Markstein's correction step).
-__device__ __forceinline__ double div_by(double a, double b, double rb) {
-  const double q0 = __dmul_rn(a, rb);
-  const double r = __fma_rn(-q0, b, a);
-  return __fma_rn(r, rb, q0);
-}
-
-// Row `ti` of one problem's P into registers.  N == T and a 32-byte aligned base take 256-bit loads.
-template <int T>
-__device__ __forceinline__ void load_row(double (&row)[T], const double* __restrict__ src, int N, bool valid,
-                                         bool vec32) {
-#pragma unroll
-  for (int j = 0; j < T; j++) row[j] = 0.0;
-  if (!valid) return;
-  if (N == T && vec32) {
-#pragma unroll
-    for (int j = 0; j < T; j += 4) {
-      asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                   : "=d"(row[j]), "=d"(row[j + 1]), "=d"(row[j + 2]), "=d"(row[j + 3])
-                   : "l"(src + j));
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < T; j++)
-      if (j < N) row[j] = __ldg(src + j);
-  }
-}
-
-// y_i = sum_j row[j] * vb[j], vb a T-entry shared vector (entries >= N are zero), in chunks of 8 so
-// that N = 24 on a 32-lane tile skips the last quarter.  Four interleaved FMA accumulators (j mod 4):
-// a single chain would cost T x 8.2 cycles of FP64 latency per product; Eigen's own gemv accumulates in
-// packets as well, so there is no bit-level order to preserve here.
-template <int T>
-__device__ __forceinline__ double row_dot(const double (&row)[T], const double* vb, int N) {
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-  for (int j0 = 0; j0 < T; j0 += 8) {
-    if (j0 < N) {
-#pragma unroll
-      for (int j = j0; j < j0 + 8; j += 4) {
-        const double2 v = *reinterpret_cast<const double2*>(vb + j);
-        const double2 w = *reinterpret_cast<const double2*>(vb + j + 2);
-        a0 = fma(row[j], v.x, a0);
-        a1 = fma(row[j + 1], v.y, a1);
-        a2 = fma(row[j + 2], w.x, a2);
-        a3 = fma(row[j + 3], w.y, a3);
-      }
-    }
-  }
-  return (a0 + a1) + (a2 + a3);
-}
-
-// Tile maximum of |a|.  Non-negative doubles order like their bit patterns, so the butterfly runs on
-// 64-bit integers (ALU pipe, no NaN fix-up code).  Every lane of the tile ends with the same bits.
-template <int T>
-__device__ __forceinline__ double tile_absmax(double a) {
-  unsigned long long k = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffULL;
-#pragma unroll
-  for (int o = T / 2; o > 0; o >>= 1) {
-    const unsigned long long g = __shfl_xor_sync(FULL_MASK, k, o);
-    k = g > k ? g : k;
-  }
-  return __longlong_as_double((long long)k);
-}
-
-// 2^-e for e = exponent of the tile's largest |w_i|: multiplying by it is exact and keeps the
-// un-normalised power iteration inside the double range.  Tile-uniform.
-template <int T>
-__device__ __forceinline__ double tile_pow2_rescale(double w) {
-  unsigned hi = (unsigned)__double2hiint(w) & 0x7fffffffu;
-#pragma unroll
-  for (int o = T / 2; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
-  const unsigned e = hi >> 20;
-  const unsigned se = (e == 0u || e >= 2046u) ? 1023u : 2046u - e;
-  return __hiloint2double((int)(se << 20), 0);
-}
-
-enum : int { PROX_NONNEG = 0, PROX_DISK = 1, PROX_BOX = 2, PROX_SIGNED_BOX = 3 };  // z-update of solveQP / solveQCQP / solveBoxQP / solveSignedBoxQP
-
-struct FwdTile {  // what one lane knows about its problem when the ADMM loop starts
-  double qi, pdiag, radius, rho, tau;
-  double ws, u0;      // start of l_2 and of the multiplier u (0 unless the warm-start extension is on)
-  double lo, hi, vs;  // box bounds and sign(v) of this element (Box / SignedBox QP)
-  const double* Prow;
-  bool valid, vprob, vec32;
-};
-
-// ---- the ADMM loop (Solver.cpp:79-121 / :538-580).  Returns this lane's element of l_2; *it_out = iterations run.
-//
-// Decisions.  With d_i = rho |l_2 - l_2_pred|_i and p_i = |l_2 - (alpha l + (1-alpha) l_2_pred)|_i the reference
-// compares the maxima  rd = max d_i,  rp = max p_i.  fl(c x) is monotone in x >= 0, so
-//     rd < eps        <=>  all_i  fl(rho |dl_i|) < eps              (one ballot)
-//     rp > 10 rd      <=>  any_i  p_i > fl(10 rd)                   (one ballot)
-//     rd > 10 rp      <=>  all_i  rd > fl(10 p_i)                   (one ballot)
-// exactly; only rd needs a real reduction.  All lanes of a tile see identical ballots, so the
-// per-problem control state (live, cpt, rho_up, rho, tau) stays tile-uniform.
-//
-// Pipelining (diagonal path).  The next iteration's arithmetic does not depend on those decisions unless
-// the tile stops or rho changes, so it is issued BEFORE the decisions of the pending iteration are
-// consumed (one speculative iteration in flight): the FP64 chain of iteration k+1 overlaps the shuffle
-// chain of iteration k.  When rho does change (a few times per solve) the speculative iteration is
-// recomputed with the new rho; when the tile stops it is dropped.  Results are identical to the
-// unpipelined order.  A finished tile keeps executing with its answer frozen until the warp is done.
-template <int T, int PROX, bool DENSE, int R>
-__device__ __forceinline__ double admm_loop(const FwdParams& p, const FwdTile& t, double* Lb, double* db,
-                                            double* vbuf, int& cur, int lane, int ti, int tile_base, int* it_out) {
-  constexpr bool QCQP = (PROX == PROX_DISK);
-  const int N = p.N;
-  const double mu = p.mu_prox, eps = p.eps;
-  const bool odd = lane & 1;
-  const unsigned tmask = (T == 32 ? 0xffffffffu : ((1u << T) - 1u)) << tile_base;
-  double rho = t.rho, tau_inc = t.tau, tau_dec = t.tau;
-  double mdiag = __dadd_rn(t.pdiag, __dadd_rn(rho, mu));  // P += (rho + mu) I   :75 / :534
-  double irho = 1.0 / rho;
-  double pinv[R];      // dense: row ti of (P + (rho+mu) I)^-1 (dead when !DENSE); R = row capacity, N <= R <= T
-  double pinvd = 0.0;  // diagonal: its only non-zero entry
-  bool live = t.vprob && p.max_iter > 0;
-  bool refac = true;
-  int rho_up = 0, cpt5 = 0;  // cpt5 = cpt % 5
-  int it = 0, itout = 0;
-  double ans = 0.0;  // l_2 of the last decided iteration of a live tile; frozen once the tile stops
-
-  struct Iter {  // one iteration's results: the new state and what the decisions need
-    double l2, u, qprox, dl, du, l;
-  };
-  // arithmetic of one iteration from state s (s.l2 == l_2_pred); reads rho / irho / Pinv
-  auto step = [&](const Iter& s, Iter& o) {
-    const double rhs = __dsub_rn(__dsub_rn(__dmul_rn(rho, s.l2), s.u), s.qprox);  // l = Pinv (rho l_2 - u - q_prox)  :80
-    double l;
-    if constexpr (DENSE) {
-      double* vb = vbuf + cur * 32;
-      vb[lane] = t.valid ? rhs : 0.0;
-      __syncwarp();
-      cur ^= 1;
-      l = row_dot<R>(pinv, vb + tile_base, N);
-    } else {
-      l = __dmul_rn(pinvd, rhs);
-    }
-    o.qprox = __dsub_rn(t.qi, __dmul_rn(mu, l));                                 // :81
-    const double relax = __dadd_rn(__dmul_rn(1.5, l), __dmul_rn(-0.5, s.l2));    // alpha l + (1-alpha) l_2_pred
-    const double z = __dadd_rn(relax, div_by(s.u, rho, irho));                   // :82   ... + u/rho
-    double l2n;
-    if (PROX == PROX_NONNEG) {
-      l2n = z < 0 ? 0.0 : z;  // cwiseMax(0)
-    } else if (PROX == PROX_BOX || PROX == PROX_SIGNED_BOX) {  // solveBoxQP :219-220 / solveSignedBoxQP :396-398
-      l2n = z < t.lo ? t.lo : z;           // cwiseMax(l_min)
-      l2n = t.hi < l2n ? t.hi : l2n;       // cwiseMin(l_max)
-      if (PROX == PROX_SIGNED_BOX) {       // v.asDiagonal() * ((v.asDiagonal() * l_2).cwiseMin(0)), v = sign(v)
-        double w = __dmul_rn(t.vs, l2n);
-        w = 0 < w ? 0.0 : w;
-        l2n = __dmul_rn(t.vs, w);
-      }
-    } else {                  // prox_circle :505-519
-      const double zo = __shfl_xor_sync(FULL_MASK, z, 1);
-      const double a0 = odd ? zo : z, a1 = odd ? z : zo;
-      const double nrm = sqrt(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)));
-      l2n = (nrm > t.radius) ? __dmul_rn(z, t.radius) / nrm : z;
-    }
-    o.du = __dsub_rn(relax, l2n);                 // l_2 - (alpha l + ...) up to sign  :86
-    o.u = __dadd_rn(s.u, __dmul_rn(rho, o.du));   // :83
-    o.dl = __dsub_rn(l2n, s.l2);                  // :84
-    o.l2 = l2n;
-    o.l = l;
-  };
-  // Pinv for the current mdiag.  Dense: all lanes take part (shuffles inside); tiles whose rho did not
-  // change recompute the same bits.  Diagonal: LLT of a diagonal matrix and the two substitutions
-  // against I give (1/s)(1/s), s = sqrt(m_ii)   :76-77, :100-101, :114-115
-  auto refactor = [&]() {
-    if constexpr (DENSE) {
-      double a[R];
-      load_row<R>(a, t.Prow, N, t.valid, t.vec32);  // L1/L2-resident re-read keeps the row out of the loop's registers
-#pragma unroll
-      for (int j = 0; j < R; j++) {
-        if (j == ti) a[j] = mdiag;
-        else if (j > ti) a[j] = 0.0;
-      }
-      tile_spd_inverse<T, R>(a, pinv, Lb, db, N, ti, tile_base);
-    } else {
-      const double a = 1.0 / sqrt(mdiag);
-      pinvd = __dmul_rn(a, a);
-    }
-  };
-  // Decide the iteration whose results are in `r`.  Returns true when rho changed for this tile.
-  auto decide = [&](const Iter& r) -> bool {
-    ++it;
-    const double adl = fabs(r.dl), pdu = fabs(r.du);
-    bool stop = (__ballot_sync(FULL_MASK, __dmul_rn(rho, adl) < eps) & tmask) == tmask;  // :88 / :548
-    const double rd = __dmul_rn(rho, tile_absmax<T>(r.dl));
-    if (QCQP) {  // also res_prim < eps + eps_rel |l|_2 (:548); the norm is reduced only when a live tile passed the dual test
-      if (__any_sync(FULL_MASK, stop && live)) {
-        const double thr = __dadd_rn(eps, __dmul_rn(1e-4, sqrt(tile_sum<T>(__dmul_rn(r.l, r.l)))));
-        const bool prim_ok = (__ballot_sync(FULL_MASK, pdu < thr) & tmask) == tmask;  // evaluated by every lane
-        stop = stop & prim_ok;
-      }
-    }
-    const bool inc = (__ballot_sync(FULL_MASK, pdu > __dmul_rn(10., rd)) & tmask) != 0u;       // :92 / :552
-    const bool dec = (__ballot_sync(FULL_MASK, rd > __dmul_rn(10., pdu)) & tmask) == tmask;    // :106 / :566
-    const bool fin = stop | (it >= p.max_iter);
-    if (live) {
-      ans = r.l2;  // :87; a finished tile keeps it (:122 / :581 return l_2)
-      if (fin) itout = it;
-    }
-    const bool cnt = live & !fin & (p.adaptive != 0) & (inc | dec);  // adaptive rho :91-120 / :551-579
-    live = live & !fin;
-    bool changed = false;
-    if (cnt) {
-      if (cpt5 == 0) {  // at most one rho update per 5 counted iterations  :93 / :553
-        if (inc) {
-          if (rho_up == -1) {
-            tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));
-            if (!QCQP) tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));  // QP decays both :95-96
-          }
-          mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(tau_inc, 1)));  // :98 / :557
-          rho = __dmul_rn(rho, tau_inc);
-          rho_up = 1;
-        } else {
-          if (rho_up == 1) {
-            if (!QCQP) tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));  // :109-110
-            tau_dec = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));
-          }
-          const double itau = 1. / tau_dec;
-          mdiag = __dadd_rn(mdiag, __dmul_rn(rho, __dsub_rn(itau, 1)));  // :112 / :571
-          rho = div_by(rho, tau_dec, itau);                             // rho /= tau_dec
-          rho_up = -1;
-        }
-        irho = 1.0 / rho;
-        changed = true;
-      }
-      cpt5 = (cpt5 == 4) ? 0 : cpt5 + 1;
-    }
-    return changed;
-  };
-
-  Iter A, B;
-  // l_2 = u = 0, q_prox = q   :67-74.  Warm-start extension (off by default, not reference behaviour): l_2 = l_2_pred =
-  // warm_start, u = -(P warm_start + q) (the multiplier of l = l_2 if warm_start were a KKT point) and the proximal term
-  // centred there, q_prox = q - mu warm_start.  With the extension off ws = u0 = 0 and these are the reference's bits.
-  A.l2 = t.ws; A.u = t.u0; A.qprox = __dsub_rn(t.qi, __dmul_rn(mu, t.ws)); A.dl = A.du = A.l = 0.0;
-  if constexpr (DENSE) {
-    while (__any_sync(FULL_MASK, live)) {  // warp ballot: leave when every problem of the group has finished
-      if (__any_sync(FULL_MASK, refac)) refactor();
-      step(A, B);
-      refac = decide(B);
-      A = B;
-    }
-  } else {
-    refactor();
-    step(A, B);  // iteration 1, undecided
-    // body(P, Q): Q = speculative iteration from P's state; decide P; on a rho change recompute Q
-    auto body = [&](Iter& P, Iter& Q) {
-      step(P, Q);
-      const bool changed = decide(P);
-      if constexpr (QCQP) {  // step shuffles (prox_circle): warp-uniform redo; unchanged tiles recompute the same bits
-        if (__any_sync(FULL_MASK, changed)) {
-          if (changed) refactor();
-          step(P, Q);
-        }
-      } else if (changed) {  // QP: step is lane-local, only the tiles whose rho changed redo it
-        refactor();
-        step(P, Q);
-      }
-    };
-    while (true) {  // ping-pong between the two register sets instead of copying them
-      if (!__any_sync(FULL_MASK, live)) break;
-      body(B, A);
-      if (!__any_sync(FULL_MASK, live)) break;
-      body(A, B);
-    }
-  }
-  *it_out = itout;
-  return ans;
-}
-
-// One group (32/T consecutive problems starting at `first`, those below `bend`) solved by one warp: the whole
-// forward of the generic path.  wsm = this warp's FwdSmem<T>::per_warp_doubles of shared scratch.
-template <int T, int PROX, int R = T>
-__device__ __forceinline__ void solve_group(const FwdParams& p, long long first, long long bend, int lane,
-                                            double* wsm) {
-  constexpr bool QCQP = (PROX == PROX_DISK);
-  const int N = p.N;
-  const int ti = lane % T;
-  const int tp = lane / T;
-  const int tile_base = tp * T;
-  const long long prob = first + tp;
-
-  FwdTile t;
-  t.vprob = prob < bend;
-  t.valid = t.vprob && ti < N;
-  t.vec32 = (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0;
-  t.Prow = p.P + (prob * N + ti) * N;
-
-  double* Lb = wsm + tp * T * T;               // [T][T] Cholesky factor of this tile
-  double* vbuf = wsm + 32 * T;                 // [2][32] gemv operand, double-buffered
-  double* db = wsm + 32 * T + 64 + tile_base;  // [T] reciprocal pivots
-
-  // ---- inputs straight into registers
-  double prow[R];
-  load_row<R>(prow, t.Prow, N, t.valid, t.vec32);
-  t.qi = t.valid ? __ldg(p.q + prob * N + ti) : 0.0;
-  t.ws = (p.warm != nullptr && t.valid) ? __ldg(p.warm + prob * N + ti) : 0.0;
-  t.radius = 0.0;
-  if (QCQP) {
-    const int nc = N >> 1;
-    if (t.valid)  // mul_n = l_n o mu   pybindings.cpp:57
-      t.radius = __dmul_rn(__ldg(p.l_n + prob * nc + (ti >> 1)), __ldg(p.mu + prob * nc + (ti >> 1)));
-  }
-  t.lo = t.hi = t.vs = 0.0;
-  if (PROX == PROX_BOX || PROX == PROX_SIGNED_BOX) {
-    if (t.valid) {
-      t.lo = __ldg(p.lo + prob * N + ti);
-      t.hi = __ldg(p.hi + prob * N + ti);
-      if (PROX == PROX_SIGNED_BOX) {
-        const double v = __ldg(p.vsign + prob * N + ti);
-        t.vs = v > 0 ? 1.0 : (v < 0 ? -1.0 : 0.0);  // v.cwiseSign()  Solver.cpp:391
-      }
-    }
-  }
-  t.pdiag = 1.0;
-  bool nz = false;
-#pragma unroll
-  for (int j = 0; j < R; j++) {
-    if (j == ti) t.pdiag = t.valid ? prow[j] : 1.0;
-    else nz |= (prow[j] != 0.0);
-  }
-  const bool dense = __any_sync(FULL_MASK, nz);  // warp-uniform: the whole group takes one path
-  // hand-off to the backward: the diagonal of a problem solved on the diagonal path, NaN otherwise
-  if (p.state != nullptr && t.valid) p.state[prob * N + ti] = dense ? __longlong_as_double(0x7ff8000000000000LL) : t.pdiag;
-
-  int cur = 0;  // gemv double buffer: one __syncwarp per product (writes of step k+2 are fenced by step k+1's)
-  if (dense) {  // zero the padded scratch once; entries with an index >= N are never written afterwards
-    for (int i = lane; i < FwdSmem<T>::per_warp_doubles; i += 32) wsm[i] = 0.0;
-    __syncwarp();
-  }
-  auto matvec = [&](double v) -> double {
-    if (!dense) return __dmul_rn(t.pdiag, v);
-    double* vb = vbuf + cur * 32;
-    vb[lane] = v;
-    __syncwarp();
-    cur ^= 1;
-    return row_dot<R>(prow, vb + tile_base, N);
-  };
-
-  t.u0 = 0.0;
-  if (p.warm != nullptr) {  // warp-uniform
-    const double pw = matvec(t.valid ? t.ws : 0.0);
-    if (t.valid) t.u0 = -__dadd_rn(pw, t.qi);
-  }
-
-  // ---- power_iteration (Solver.cpp:46-59): fixed count, 10 for the QP (:71), 100 for the QCQP (:530).
-  // The reference divides by |Pv| after every product; the direction of v does not depend on those
-  // scalings, so here the iterate is only rescaled by an exact power of two every 4th product and
-  // normalised once at the end: L agrees with the reference to rounding.
-  double Lmax;
-  {
-    double w = t.valid ? 1.0 : 0.0;
-    const int K = QCQP ? 100 : 10;
-    for (int k = 0; k < K; k++) {
-      w = matvec(w);
-      if ((k & 3) == 3 || k == K - 1) w = __dmul_rn(w, tile_pow2_rescale<T>(w));
-    }
-    const double z = tile_sum<T>(__dmul_rn(w, w));
-    const double v = (z > 0) ? w / sqrt(z) : w;
-    Lmax = tile_sum<T>(__dmul_rn(v, matvec(v)));  // l_max = v . (P v)   :56-57
-  }
-
-  // ---- rho / tau initialisation (Solver.cpp:72-73, :531-532).  One pow() per lane: even lanes take
-  // the .4 exponent, odd lanes the .15 exponent, neighbours swap.
-  {
-    const double mu = p.mu_prox;
-    const double pw = pow(Lmax / mu, (lane & 1) ? .15 : .4);
-    const double pw4 = __shfl_sync(FULL_MASK, pw, lane & ~1);
-    t.tau = __shfl_sync(FULL_MASK, pw, lane | 1);
-    t.rho = __dmul_rn(sqrt(__dmul_rn(mu, Lmax)), pw4);
-  }
-
-  int it;
-  const double x = dense ? admm_loop<T, PROX, true, R>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it)
-                         : admm_loop<T, PROX, false, R>(p, t, Lb, db, vbuf, cur, lane, ti, tile_base, &it);
-  if (t.valid) p.x[prob * N + ti] = x;
-  if (t.vprob && ti == 0 && p.iters) p.iters[prob] = it;
-}
 
 #ifndef DQ_FWD_WPS24
 #define DQ_FWD_WPS24 16  // resident warps per SM the 32-lane, 24-entry instance is sized for
@@ -872,7 +470,13 @@ static cudaError_t launch_fwd_p(const FwdParams& p, int T, cudaStream_t stream) 
 }
 
 // ---- diagonal fast path launch: a persistent grid (every resident warp slot of the device), chunks balanced over it
-static int g_fwd_path = 0;  // 0 = automatic, 1 = generic kernel only, 2 = persistent kernel wherever it applies (tests)
+static int g_fwd_path = 0;  // 0 = automatic, 1 = generic kernel only, 2 = persistent tile kernel wherever it applies, 3 = thread-per-problem kernel wherever it applies (tests)
+static long long g_tpp_min_batch = 32768;  // automatic path: batches of at least this many N == 8 problems take the thread-per-problem kernel
+long long set_tpp_min_batch(long long b) {
+  const long long old = g_tpp_min_batch;
+  g_tpp_min_batch = b;
+  return old;
+}
 int set_fwd_path(int path) {
   const int old = g_fwd_path;
   g_fwd_path = path;
@@ -910,8 +514,12 @@ cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t st
   // N == 8, QP / Box prox: persistent CTAs, diagonal batches on refilled tile slots, dense batches via solve_group.
   // The disk prox (QCQP) stays on the generic kernel: its iteration counts are too even for the refill to pay
   // (measured: 116 us vs 98 us per 65536 diagonal problems).  g_fwd_path == 2 forces the persistent kernel for it too.
-  if (g_fwd_path != 1 && p.N == 8 && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0 && p.warm == nullptr &&
-      (prox != PROX_DISK || g_fwd_path == 2)) {  // (warm-started batches: generic kernel; their iteration counts are short and even)
+  const bool n8 = p.N == 8 && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0 && p.warm == nullptr;
+  // N == 8, large batches: one problem per thread (admm_fwd_tpp.cu) -- 2.4x fewer instructions per solve than the tile
+  // kernels, but a lane owns a whole problem, so it needs >= ~1 problem per thread slot of the device to pay
+  if (n8 && (g_fwd_path == 3 || (g_fwd_path == 0 && p.B >= g_tpp_min_batch && prox != PROX_DISK)))
+    return launch_tpp8(p, prox, stream);
+  if (g_fwd_path != 1 && n8 && (prox != PROX_DISK || g_fwd_path == 2)) {  // (warm-started batches: generic kernel; their iteration counts are short and even)
     switch (prox) {
       case PROX_NONNEG: return launch_diag8<PROX_NONNEG>(p, stream);
       case PROX_DISK: return launch_diag8<PROX_DISK>(p, stream);

@@ -361,7 +361,19 @@ int dq_max_n(void) { return DQ_MAX_N; }
 int dq_last_cuda_error(void) { return g_last_cuda_error; }
 int64_t dq_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 void dq_host_release(void) { host_release_all(); }
-int dq_set_forward_path(int path) { return dq::set_fwd_path(path == 1 || path == 2 ? path : 0); }
+int dq_set_forward_path(int path) { return dq::set_fwd_path(path >= 1 && path <= 3 ? path : 0); }
+int dq_selftest_inverse(const double* x, int64_t n, uint64_t* bad, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !bad))) return DQ_ERR_BAD_ARG;
+  cudaError_t e = dq::launch_selftest_inverse(x, n, reinterpret_cast<unsigned long long*>(bad), (cudaStream_t)stream);
+  return e == cudaSuccess ? DQ_OK : cuda_fail(e);
+}
+int64_t dq_set_forward_tuning(int32_t key, int64_t value) {
+  switch (key) {
+    case 0: return dq::set_tpp_cap_it((int)value);
+    case 1: return dq::set_tpp_min_batch(value);
+    default: return -1;
+  }
+}
 
 const char* dq_error_string(int code) {
   switch (code) {

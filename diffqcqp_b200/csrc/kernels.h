@@ -68,7 +68,13 @@ inline int tile_width(int N) { return N <= 8 ? 8 : (N <= 16 ? 16 : 32); }
 size_t fwd_smem_bytes(int T);
 // prox: 0 = x >= 0 (solveQP), 1 = per-contact disks (solveQCQP), 2 = box (solveBoxQP), 3 = box + sign (solveSignedBoxQP)
 cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t stream);
-int set_fwd_path(int path);  // 0 = automatic, 1 = generic kernel only; returns the previous value
+int set_fwd_path(int path);  // 0 = automatic, 1 = generic kernel, 2 = persistent tile kernel, 3 = thread-per-problem kernel (N == 8); returns the previous value
+// N == 8, 32-byte aligned P, no warm start: one problem per thread (admm_fwd_tpp.cu)
+cudaError_t launch_tpp8(const FwdParams& p, int prox, cudaStream_t stream);
+long long set_tpp_min_batch(long long b);  // automatic path: smallest batch that takes the thread-per-problem kernel; returns the previous value
+int set_tpp_cap_it(int v);  // iterations after which the thread-per-problem kernel parks a problem for its tile phase; returns the previous value
+// bad[0..2] += mismatches of fast_sqrt / fast_rcp / fast_rcp(fast_sqrt) against the library's, bad[3] += values outside the fast range
+cudaError_t launch_selftest_inverse(const double* x, long long n, unsigned long long* bad, cudaStream_t stream);
 cudaError_t launch_qp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_boxqp_bwd(const BoxBwdParams& p, int T, cudaStream_t stream);

@@ -76,7 +76,7 @@ def _stream_ptr(device) -> int:
 
 
 def _as_dev(t: torch.Tensor, device, name: str) -> torch.Tensor:
-    """fp64, contiguous, on `device`, 16-byte aligned (the bulk-copy path wants that)."""
+    """fp64, contiguous, on `device`, 32-byte aligned (the 256-bit load / store paths want that)."""
     if not isinstance(t, torch.Tensor):
         raise ValueError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
     if not t.dtype.is_floating_point:
@@ -86,7 +86,7 @@ def _as_dev(t: torch.Tensor, device, name: str) -> torch.Tensor:
         t = t.to(device=device, dtype=torch.float64, non_blocking=True)
     if not t.is_contiguous():
         t = t.contiguous()
-    if t.data_ptr() % 16:
+    if t.data_ptr() % 32:
         t = t.clone(memory_format=torch.contiguous_format)
     return t
 

@@ -18,8 +18,8 @@
  * legacy default stream); they only enqueue work and never synchronise.  *_host entry points take
  * HOST pointers, pipeline the copies with the solve and return when the outputs are in host memory.
  *
- * Pointers must be 8-byte aligned; 16-byte aligned base pointers enable the bulk-copy (TMA) stage-in
- * (otherwise a slower element-wise stage-in is used, same results).
+ * Pointers must be 8-byte aligned; 32-byte aligned base pointers (and N in {8,16,24,32}) take the 256-bit
+ * load / store path (otherwise scalar accesses are used, same results).
  *
  * Return value: DQ_OK or a DQ_ERR_* code (dq_error_string gives text).  Nothing is thrown.
  * There is NO CPU fallback: without a CUDA device every compute entry point returns DQ_ERR_CUDA.
@@ -178,12 +178,31 @@ void dq_host_release(void);
 int64_t dq_launch_count(void);
 
 /*
- * Forward kernel selection (process-wide; for tests and A/B timing).  0 = automatic: the QP / Box QP with N == 8 and a
- * 32-byte aligned P runs the persistent-CTA kernel (diagonal batches on refilled tile slots), everything else the
- * generic kernel.  1 = generic kernel only.  2 = persistent kernel wherever it applies (also the QCQP at N == 8).
+ * Forward kernel selection (process-wide; for tests and A/B timing).  0 = automatic: at N == 8 with a 32-byte aligned P
+ * and no warm start, batches of >= 32768 QP / Box QP problems run the thread-per-problem kernel (one problem per thread,
+ * stragglers finished on 8-lane tiles), smaller ones the persistent-CTA tile kernel (diagonal batches on refilled tile
+ * slots); everything else the generic kernel.  1 = generic kernel only.  2 = persistent tile kernel wherever it applies
+ * (also the QCQP at N == 8).  3 = thread-per-problem kernel wherever it applies (also the QCQP at N == 8, any batch size).
  * The kernels produce bit-identical results on batches that are all diagonal or all dense.  Returns the previous setting.
  */
 int dq_set_forward_path(int path);
+
+/*
+ * Tuning knobs of the forward kernels (process-wide; for tests and A/B timing; results do not depend on them).
+ *   key 0: iterations after which the thread-per-problem kernel parks a still-running problem for its tile phase
+ *          (default 48; 0 = never)
+ *   key 1: smallest batch the automatic path gives to the thread-per-problem kernel (default 32768)
+ * Returns the previous value, -1 for an unknown key.
+ */
+int64_t dq_set_forward_tuning(int32_t key, int64_t value);
+
+/*
+ * Self-test of the branch-free square root / reciprocal the thread-per-problem forward uses for (P + (rho+mu) I)^-1
+ * (Solver.cpp:76-77 for diagonal P) against the CUDA library's IEEE sqrt() and division: x = n DEVICE doubles,
+ * bad = 4 DEVICE counters, incremented by the number of x whose sqrt / reciprocal / reciprocal-of-sqrt bits differ
+ * (bad[0..2], must stay 0) and by the number of x outside the range the fast versions are used for (bad[3]).
+ */
+int dq_selftest_inverse(const double* x, int64_t n, uint64_t* bad, void* stream);
 
 #ifdef __cplusplus
 }
