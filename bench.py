@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true", help="(N>1) skip the BASELINE configs[4] section (B=262144/GPU N=16 QCQP, "
+                                                          "shard-resident and scatter-inclusive)")
     ap.add_argument("--scatter", action="store_true",
                     help="(N>1) also time the scatter-inclusive step: rank 0 holds all N*B problems, NCCL scatter of "
                          "(P,q[,l_n,mu],grad_l), solve, NCCL gather of x* and grad_q")
@@ -89,6 +91,59 @@ def alg_bytes(kind, N):
 
     f = wl.qp_bytes if kind == "qp" else wl.qcqp_bytes
     return f(N, True, False), f(N, False, True)
+
+
+def rotating_sets(kind, B, N, streams):
+    """R input/output sets the GPU arm rotates through: total input footprint > 126 MB L2, at least one per stream, a
+    multiple of the stream count (a set is then always used on the same stream: no two streams ever share buffers)."""
+    nc = N // 2
+    in_bytes_per_set = 8 * B * (2 * N * N + 4 * N + (4 * nc if kind == "qcqp" else 0))
+    R = max(2, int(-(-200e6 // in_bytes_per_set)) + 1)
+    S = max(1, min(streams, 16))
+    R = min(max(R, S), 16)
+    S = min(S, R)
+    R = -(-R // S) * S
+    return R, S, in_bytes_per_set
+
+
+def common_config(args, world):
+    """The part of `config` both arms (--impl b200 / reference) print identically: what is solved, how it is sharded and
+    how the GPU arm keeps its inputs out of L2."""
+    kind, B, N, kw, desc = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    R, S, in_bytes = rotating_sets(kind, B, N, args.streams)
+    return {"workload": desc, "name": args.workload, "B_per_gpu": B, "N": N, "eps": EPS, "max_iter": MAX_ITER,
+            "sharding": f"batch-sharded x{world}, no data-path collective",
+            "l2_policy": f"GPU arm: {R} rotating input sets, {R * in_bytes / 1e6:.0f} MB footprint > 126 MB L2; "
+                         "CPU arm: a bounded sample of the same batch per step"}
+
+
+FP64_PEAK_WARP_INST_PER_CLK_PER_SM = 59.6 / 32  # measured: 59.6 DFMA lane-ops/clk/SM (profiles/r01_micro_fp64_latency.txt, r02_micro_mufu64.txt)
+
+
+def fp64_roofline(workload, kernel, ms, sm_mhz, sms=148):
+    """FP64 side of the roofline for one kernel launch of `ms` milliseconds, from the instruction counts an ncu pass over
+    the same command recorded in profiles/fp64_ops.json (thread-level DADD/DMUL/DFMA and FP64-pipe warp instructions per
+    launch).  peak = measured 59.6 FP64 lane-ops/clk/SM x SMs x the SM clock sampled during the timed region."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_ops.json")) as fh:
+            ops = json.load(fh).get(workload, {}).get(kernel)
+    except Exception:
+        ops = None
+    if not ops or not ms:
+        return None
+    clk = (sm_mhz or 1965.0) * 1e6
+    lane_ops = ops["dadd"] + ops["dmul"] + ops["dfma"]
+    flops = ops["dadd"] + ops["dmul"] + 2 * ops["dfma"]
+    peak_lane = 32 * FP64_PEAK_WARP_INST_PER_CLK_PER_SM * sms * clk
+    peak_warp = FP64_PEAK_WARP_INST_PER_CLK_PER_SM * sms * clk
+    t = ms * 1e-3
+    return {"unit": "TFLOP/s (FMA = 2)", "achieved": flops / t / 1e12, "peak": 2 * peak_lane / 1e12,
+            "frac_lane_ops": lane_ops / t / peak_lane,          # useful FP64 lane-operations against the pipe's lane rate
+            "frac_pipe": ops["fp64_warp_inst"] / t / peak_warp,  # FP64-pipe issue slots used (partially filled warps count whole)
+            "fp64_lane_ops_per_launch": lane_ops, "fp64_warp_inst_per_launch": ops["fp64_warp_inst"],
+            "warp_inst_per_launch": ops.get("warp_inst"), "source": "profiles/fp64_ops.json (ncu counters of the same command)"}
 
 
 def hbm_peak():
@@ -182,6 +237,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU baseline
+CPU_BUILD_NOTE = {
+    "reference": "the reference's own qcqplib/Solver.cpp, unmodified, compiled with -O3 -fopenmp against oracle/eigen_standin "
+                 "(a plain-loop stand-in for the Eigen API it uses: real Eigen is absent here, so no packetised Eigen kernels)",
+    "port": "oracle/dq_oracle.c, the line-by-line C restatement of Solver.cpp (-O3 -fopenmp)",
+}
+
+
 def cpu_engine(use_ref=True):
     """The CPU implementation timed as the baseline: the reference's own Solver.cpp build (oracle/_ref,
     kind "reference") when that library travelled with the repo, else the oracle restatement ("port")."""
@@ -284,13 +346,105 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "QP/QCQP fwd+bwd solves/sec", "value": value, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "name": args.workload, "B": B, "N": N, "eps": EPS, "max_iter": MAX_ITER,
-                   "step": sample},
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": ckind, "sample": sample},
+        "config": common_config(args, args.gpus),
+        "detail": {"step": sample},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": ckind, "sample": sample,
+                         "build": CPU_BUILD_NOTE[ckind]},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- BASELINE configs[4] at N > 1
+def run_cfg5(L, dev, rank, world, barrier, steps=6, scatter_steps=3):
+    import torch
+    import torch.distributed as dist
+    from diffqcqp_b200 import _lib, shard, workloads as wl
+
+    B5, N5 = 262144, 16
+    nc = N5 // 2
+    keys = ["P", "q", "l_n", "mu", "g"]
+    sets = []
+    for r in range(2):  # two rotating sets: 2 x 0.6 GB of inputs, far beyond L2
+        d = dict(zip(keys, (t.to(dev) for t in wl.qcqp_dense(B5, N5, seed=7000 + 10 * rank + r))))
+        d.update(x=torch.empty((B5, N5, 1), dtype=torch.float64, device=dev), st=torch.empty((B5, N5, 1), dtype=torch.float64, device=dev),
+                 gP=torch.empty((B5, N5, N5), dtype=torch.float64, device=dev), gq=torch.empty((B5, N5, 1), dtype=torch.float64, device=dev),
+                 gl=torch.empty((B5, nc, 1), dtype=torch.float64, device=dev), gm=torch.empty((B5, nc, 1), dtype=torch.float64, device=dev))
+        sets.append(d)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(d):
+        sp = stream.cuda_stream
+        _lib.check(L.dq_qcqp_forward_ex(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(), None,
+                                        d["x"].data_ptr(), None, d["st"].data_ptr(), B5, N5, EPS, MU_PROX, MAX_ITER, 1, sp), "forward")
+        _lib.check(L.dq_qcqp_backward_ex2(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(),
+                                          d["x"].data_ptr(), d["g"].data_ptr(), d["st"].data_ptr(), d["gP"].data_ptr(),
+                                          d["gq"].data_ptr(), d["gl"].data_ptr(), d["gm"].data_ptr(), None, None, B5, N5, sp), "backward")
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(n):
+            fn(k)
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for k in range(2):
+        step(sets[k % 2])
+    resident_ms = timed(lambda k: step(sets[k % 2]), steps)
+
+    # scatter-inclusive: rank 0 holds all world * B5 problems
+    full = [torch.cat([sets[0][k]] * world, 0) for k in keys] if rank == 0 else None
+    trailing = [tuple(sets[0][k].shape[1:]) for k in keys]
+    d = sets[1]
+    t_sc = [0.0]
+
+    def scatter_step(_k):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        parts = shard.scatter_batch(full, B5 * world, src=0, device=dev, trailing=trailing)
+        a1.record(stream)
+        loc = dict(zip(keys, parts))
+        loc.update(x=d["x"], st=d["st"], gP=d["gP"], gq=d["gq"], gl=d["gl"], gm=d["gm"])
+        step(loc)
+        shard.gather_batch(loc["x"], B5 * world, dst=0)
+        shard.gather_batch(loc["gq"], B5 * world, dst=0)
+        torch.cuda.synchronize(dev)
+        t_sc[0] += a0.elapsed_time(a1)
+
+    scatter_step(0)
+    t_sc[0] = 0.0
+    scatter_ms = timed(scatter_step, scatter_steps)
+    sc_only = torch.tensor([t_sc[0] / scatter_steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(sc_only, op=dist.ReduceOp.MAX)
+    egress = sum(int(f.numel()) * 8 for f in full) * (world - 1) // world if rank == 0 else 0
+    eg = torch.tensor([float(egress)], dtype=torch.float64, device=dev)
+    dist.all_reduce(eg, op=dist.ReduceOp.MAX)
+    egress = int(eg.item())
+    fb = 8 * (N5 * N5 + 3 * N5 + 2 * nc) + 8 * N5  # forward incl. the hand-off write
+    bb = 8 * (2 * N5 * N5 + 4 * N5 + 4 * nc)
+    peak, _ = hbm_peak()
+    out = {"workload": f"B={B5 * world} N={N5} QCQP (8 contacts) fp64 batch-sharded across {world} x B200 (BASELINE configs[4]: 2097152 at 8)",
+           "B_per_gpu": B5, "B_total": B5 * world,
+           "shard_resident": {"ms_per_step": resident_ms, "value": B5 * world / (resident_ms * 1e-3), "unit": "solves/s",
+                              "step_frac_hbm": (fb + bb) * B5 / (resident_ms * 1e-3) / 1e9 / peak},
+           "scatter_inclusive": {"ms_per_step": scatter_ms, "value": B5 * world / (scatter_ms * 1e-3), "unit": "solves/s",
+                                 "scatter_ms": float(sc_only.item())},
+           "root_egress_bytes": egress,
+           "nccl_gbs": egress / (float(sc_only.item()) * 1e-3) / 1e9 if sc_only.item() > 0 else None,
+           "nccl_reference_gbs": {"nvlink5_nominal_per_direction": 900.0, "measured_peer_copy_per_direction": 770.0},
+           "note": "scatter = grouped NCCL send/recv (ncclGroup of isend/irecv, diffqcqp_b200/shard.py) of (P, q, l_n, mu, grad_l) from "
+                   "rank 0; gather of x* and grad_q (grad_P stays sharded).  Every byte bound for another rank leaves rank 0 exactly "
+                   "once, so its egress -- (world-1)/world of the batch -- is the floor for any scatter schedule (a tree moves the "
+                   "same bytes out of the root); the achieved rate against the 900 GB/s per direction of its NVLink ports is nccl_gbs."}
+    del sets, full
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -333,9 +487,7 @@ def run_b200_arm(args):
     if handoff:
         fb, bb = fb + 8 * N, bb - 8 * N * N + 8 * N
     # one set = inputs (P, q, grad_l [, l_n, mu]) + outputs (x, grad_P, grad_q [, grad_l_n, grad_mu])
-    in_bytes_per_set = 8 * B * (2 * N * N + 4 * N + (4 * nc if kind == "qcqp" else 0))
-    R = max(2, int(-(-200e6 // in_bytes_per_set)) + 1)  # rotating sets: total footprint > 126 MB L2
-    R = min(max(R, args.streams), 16)  # at least one set per stream, so that overlapping steps never share buffers
+    R, S, in_bytes_per_set = rotating_sets(kind, B, N, args.streams)
     sets = []
     host0 = None
     for r in range(R):
@@ -380,7 +532,6 @@ def run_b200_arm(args):
 
     # ---- streams: step k runs on stream k % S (fwd then bwd of one batch stay ordered on their stream; independent
     # batches overlap, which hides each forward launch's long-iteration tail behind the next batch's work)
-    S = max(1, min(args.streams, R))
     streams = [stream] + [torch.cuda.Stream(dev) for _ in range(S - 1)]
     sps = [st.cuda_stream for st in streams]
 
@@ -501,6 +652,47 @@ def run_b200_arm(args):
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
                "api": "dq_qp_solve_host" if kind == "qp" else "dq_qcqp_solve_host"}
 
+    # ---- the same step through the autograd surface a user of the reference calls (README.md:45-56): QPFn2.apply(...) and
+    # .backward(), with CUDA tensors (device-resident, for comparison with `value`) and with pinned CPU tensors (host
+    # buffers in, host buffers out: the chunked copy/compute pipeline of diffqcqp_b200/qcqp.py)
+    e2e_autograd = None
+    if not args.no_e2e:
+        import qcqp as surface
+
+        def autograd_step(t):
+            leaves = [v.detach().requires_grad_(True) for v in t[:-1]]
+            if kind == "qp":
+                x = surface.QPFn2.apply(leaves[0], leaves[1], None, EPS, MAX_ITER)
+            else:
+                x = surface.QCQPFn2.apply(leaves[0], leaves[1], leaves[2], leaves[3], None, EPS, MAX_ITER)
+            x.backward(t[-1])
+            return leaves[0].grad
+
+        keys = ["P", "q"] + (["l_n", "mu"] if kind == "qcqp" else []) + ["g"]
+        e2e_autograd = {"unit": "solves/s"}
+        nst = min(args.steps, 200)
+        for label, tens in (("cuda_tensors", [sets[0][k] for k in keys]), ("cpu_pinned_tensors", [h[k] for k in keys])):
+            for _ in range(3):
+                autograd_step(tens)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nst):
+                autograd_step(tens)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            if distributed:
+                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            e2e_autograd[label] = {"value": B * world * nst / dt, "ms_per_step": 1e3 * dt / nst}
+        e2e_autograd["api"] = ("QPFn2" if kind == "qp" else "QCQPFn2") + ".apply(...) + .backward(grad_l), wall clock incl. autograd and allocator"
+
+    # ---- BASELINE configs[4] (N>1): B = 2,097,152 / 8 = 262144 QCQPs of N = 16 per GPU, shard-resident and with the
+    # NCCL scatter of (P, q, l_n, mu, grad_l) from rank 0 and the gather of x*, grad_q back
+    cfg5 = None
+    if distributed and not args.no_cfg5:
+        cfg5 = run_cfg5(L, dev, rank, world, barrier)
+
     # ---- scatter-inclusive step (N>1, --scatter): rank 0 owns all world*B problems; NCCL point-to-point scatter of the
     # inputs, the sharded solve, gather of x* and grad_q (grad_P stays sharded: it is 8N^2 bytes per problem)
     scatter_line = None
@@ -549,7 +741,10 @@ def run_b200_arm(args):
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        fwd_name = "admm_fwd_diag8_kernel" if (kind == "qp" and N == 8) else "admm_fwd_kernel"  # launch_admm_fwd's dispatch
+        # launch_admm_fwd's dispatch (csrc/admm_fwd.cu): N == 8 QPs -> thread-per-problem kernel from 65536 problems, the
+        # persistent tile kernel below that; everything else the generic kernel
+        fwd_name = ("admm_fwd_tpp8_kernel" if B >= 65536 else "admm_fwd_diag8_kernel") if (kind == "qp" and N == 8) else "admm_fwd_kernel"
+        sm_mhz = (clocks or {}).get("sm_mhz")
         dom = fwd_name if fwd_avg >= bwd_avg else ("qp_bwd_kernel" if kind == "qp" else "qcqp_bwd_kernel")
         dom_ms = max(fwd_avg, bwd_avg)
         dom_bytes = (fb if fwd_avg >= bwd_avg else bb) * B
@@ -566,11 +761,9 @@ def run_b200_arm(args):
             "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "name": args.workload, "B_per_gpu": B, "N": N, "eps": EPS,
-                       "max_iter": MAX_ITER, "sharding": f"batch-sharded x{world}, no data-path collective",
-                       "streams": S, "single_stream_ms_per_step": serial_ms_per_step,
-                       "fwd_bwd_handoff": handoff,
-                       "l2_policy": f"{R} rotating input sets, {R * in_bytes_per_set / 1e6:.0f} MB footprint > 126 MB L2"},
+            "config": common_config(args, world),
+            "detail": {"streams": S, "single_stream_ms_per_step": serial_ms_per_step, "fwd_bwd_handoff": handoff,
+                       "forward_kernel": fwd_name},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "alg_bytes_per_solve": {"fwd": fb, "bwd": bb},
@@ -579,6 +772,10 @@ def run_b200_arm(args):
                          "kernel_ms_sustained": {"fwd": fwd_sus, "bwd": bwd_sus},
                          "kernel_frac_sustained": {"fwd": fb * B / (fwd_sus * 1e-3) / 1e9 / peak,
                                                    "bwd": bb * B / (bwd_sus * 1e-3) / 1e9 / peak},
+                         "fp64": {"fwd": fp64_roofline(args.workload, fwd_name, fwd_avg, sm_mhz),
+                                  "fwd_sustained": fp64_roofline(args.workload, fwd_name, fwd_sus, sm_mhz),
+                                  "bwd": fp64_roofline(args.workload, "qp_bwd_kernel" if kind == "qp" else "qcqp_bwd_kernel", bwd_avg, sm_mhz)}
+                         if not args.batch else None,
                          "step_achieved_gbs": step_achieved, "step_frac": step_achieved / peak,
                          "overlapped_step_ms": total_ms / args.steps,
                          "note": "the forward kernel is FP64-issue/latency bound, not HBM bound (DESIGN.md section 5.1); "
@@ -587,12 +784,15 @@ def run_b200_arm(args):
                                  "region's streams, where the next batch's work fills the GPU behind the stragglers (for the "
                                  "HBM-bound backward that figure also overlaps one launch's write-back with the next launch, "
                                  "so its fraction can exceed 1)"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "e2e": e2e, "e2e_autograd": e2e_autograd, "gpu_launches": launches, "clocks": clocks,
         }
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
         if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (the reference arm covers N>1)
             eng, ckind, a, n, reps = cpu_sample(kind, host0, B, 10.0, args.cpu_sample)
             dt = sum(cpu_pass(eng, kind, a) for _ in range(reps))
             line["cpu_baseline"] = {"value": n * reps / dt, "unit": "solves/s", "cores": host_threads(), "kind": ckind,
+                                    "build": CPU_BUILD_NOTE[ckind],
                                     "sample": f"{reps} x (fwd+bwd over the first {n} of {B} problems), OpenMP over problems, {dt:.1f} s"}
             line["cpu_baseline"]["as_shipped"] = as_shipped_loop(kind, host0, eng)
         if scatter_line is not None:

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("DQ_LIB_PATH") or os.path.join(_HERE, "libdiffqcqp_b20
 SYMBOLS = [
     "dq_version", "dq_build_arch", "dq_error_string", "dq_last_cuda_error", "dq_max_n",
     "dq_qp_forward", "dq_qp_backward", "dq_qcqp_forward", "dq_qcqp_backward",
-    "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release", "dq_qcqp_backward_ex", "dq_boxqp_forward", "dq_boxqp_backward",
+    "dq_qp_solve_host", "dq_qcqp_solve_host", "dq_launch_count", "dq_host_release", "dq_qcqp_backward_ex", "dq_boxqp_forward", "dq_boxqp_backward", "dq_boxqp_backward_ex",
     "dq_set_forward_path", "dq_set_forward_tuning", "dq_selftest_inverse", "dq_qp_forward_ex", "dq_qp_backward_ex",
     "dq_qcqp_forward_ex", "dq_qcqp_backward_ex2",
 ]
@@ -69,6 +69,8 @@ def load():
     L.dq_boxqp_forward.argtypes = [_vp] * 8 + [_i64, _i32, _f64, _f64, _i32, _i32, _vp]
     L.dq_boxqp_backward.restype = ctypes.c_int
     L.dq_boxqp_backward.argtypes = [_vp] * 10 + [_i64, _i32, _vp]
+    L.dq_boxqp_backward_ex.restype = ctypes.c_int
+    L.dq_boxqp_backward_ex.argtypes = [_vp] * 12 + [_i64, _i32, _vp]
     L.dq_qcqp_backward_ex.restype = ctypes.c_int
     L.dq_qcqp_backward_ex.argtypes = [_vp] * 12 + [_i64, _i32, _vp]
     L.dq_qcqp_forward_ex.restype = ctypes.c_int
@@ -97,7 +99,7 @@ def launch_count() -> int:
 
 def set_forward_path(path: int) -> int:
     """Forward kernel selection (process-wide): 0 = automatic (N == 8 QP / Box QP: thread-per-problem kernel for batches of
-    >= 32768 problems, persistent-CTA tile kernel below that), 1 = generic kernel only (e.g. for batches known to have dense
+    >= 65536 problems, persistent-CTA tile kernel below that), 1 = generic kernel only (e.g. for batches known to have dense
     P at N == 8), 2 = persistent tile kernel wherever it applies, 3 = thread-per-problem kernel wherever it applies.
     Returns the previous setting.  Results do not depend on it (bit-identical on all-diagonal / all-dense batches)."""
     return int(load().dq_set_forward_path(int(path)))

@@ -471,7 +471,7 @@ static cudaError_t launch_fwd_p(const FwdParams& p, int T, cudaStream_t stream) 
 
 // ---- diagonal fast path launch: a persistent grid (every resident warp slot of the device), chunks balanced over it
 static int g_fwd_path = 0;  // 0 = automatic, 1 = generic kernel only, 2 = persistent tile kernel wherever it applies, 3 = thread-per-problem kernel wherever it applies (tests)
-static long long g_tpp_min_batch = 32768;  // automatic path: batches of at least this many N == 8 problems take the thread-per-problem kernel
+static long long g_tpp_min_batch = 65536;  // automatic path: batches of at least this many N == 8 problems take the thread-per-problem kernel
 long long set_tpp_min_batch(long long b) {
   const long long old = g_tpp_min_batch;
   g_tpp_min_batch = b;

@@ -28,21 +28,35 @@ namespace dq {
 #ifndef DQ_TPP_WARPS
 #define DQ_TPP_WARPS 4  // warps per CTA
 #endif
-#ifndef DQ_TPP_PPT
-#define DQ_TPP_PPT 2  // capacity: problems per thread a CTA's chunk may hold
-#endif
-#ifndef DQ_TPP_CTAS
-#define DQ_TPP_CTAS 3  // resident CTAs per SM the register budget is sized for
+#ifndef DQ_TPP_PPS4
+#define DQ_TPP_PPS4 7  // capacity: quarter-problems per problem slot a CTA's chunk may hold (7 -> 1.75 problems per slot)
 #endif
 constexpr int TPP_WARPS = DQ_TPP_WARPS;
 constexpr int TPP_THREADS = 32 * TPP_WARPS;
-constexpr int TPP_CAP = TPP_THREADS * DQ_TPP_PPT * 7 / 8;  // problems per CTA (224 at 4 warps: three CTAs' records fit one SM)
-constexpr int TPP_STRAG = 8 * TPP_WARPS;           // parked stragglers per CTA (two rounds of the tile phase)
-constexpr int TPP_SD = 25;                         // doubles per parked problem (l_2, u, q_prox), odd stride
+constexpr int TPP_STRAG = 8 * TPP_WARPS;  // parked stragglers per CTA (two rounds of the tile phase)
+constexpr int TPP_SD = 25;                // doubles per parked problem (l_2, u, q_prox), odd stride
 
-template <int PROX>
+// E = elements of a problem one lane holds: 8 (a thread per problem) or 4 (a lane pair).  Fewer elements per
+// lane = more instructions per solve (the per-problem scalar work is replicated, the maxima need shuffles) but fewer
+// registers and more resident warps to hide the latency of the divergent sections.
+template <int E>
+struct TppGeo {
+  static_assert(E == 8 || E == 4, "elements per lane");
+  static constexpr int T = 8 / E;                      // lanes per problem
+  static constexpr int SLOTS = TPP_THREADS / T;        // problems a CTA iterates on at a time
+  static constexpr int CAP = SLOTS * DQ_TPP_PPS4 / 4;  // problems per CTA
+  static constexpr unsigned LEADERS = T == 1 ? 0xffffffffu : (T == 2 ? 0x55555555u : 0x11111111u);  // first lane of each slot
+#ifdef DQ_TPP_CTAS
+  static constexpr int CTAS = DQ_TPP_CTAS;
+#else
+  static constexpr int CTAS = E == 8 ? 3 : (E == 4 ? 5 : 8);  // resident CTAs per SM the register budget is sized for
+#endif
+};
+
+template <int PROX, int E>
 struct TppRec {  // one problem's record in shared memory, in doubles
   static constexpr bool BOX = (PROX == PROX_BOX || PROX == PROX_SIGNED_BOX);
+  static constexpr int CAP = TppGeo<E>::CAP;
   static constexpr int Q = 0;      // q_i                       (tile phase: this lane's tau_inc)
   static constexpr int M = 8;      // p_ii, then p_ii + (rho + mu)
   static constexpr int PINV = 16;  // 1 / m_ii as the reference forms it   (tile phase: this lane's tau_dec)
@@ -55,9 +69,9 @@ struct TppRec {  // one problem's record in shared memory, in doubles
   static constexpr int X2 = 48;    // sign(v) [8]
   static constexpr int USED = PROX == PROX_NONNEG ? 32 : (PROX == PROX_DISK ? 36 : (PROX == PROX_BOX ? 48 : 56));
   static constexpr int D = USED | 1;  // odd stride: thread j reading rec[j * D + i] hits 32 distinct bank pairs
-  static constexpr size_t bytes = (size_t)(TPP_CAP * D + TPP_STRAG * TPP_SD) * sizeof(double) +
-                                  (size_t)(2 * TPP_CAP + 4 * TPP_STRAG + TPP_THREADS + 8 + 32) * sizeof(int);
-  static_assert(TPP_CAP * D >= TPP_WARPS * FwdSmem<8>::per_warp_doubles, "the records double as the generic path's scratch");
+  static constexpr size_t bytes = (size_t)(CAP * D + TPP_STRAG * TPP_SD) * sizeof(double) +
+                                  (size_t)(2 * CAP + 4 * TPP_STRAG + TPP_THREADS + 8 + 32) * sizeof(int);
+  static_assert(CAP * D >= TPP_WARPS * FwdSmem<8>::per_warp_doubles, "the records double as the generic path's scratch");
 };
 
 // sum of eight values in the order of tile_sum<8>'s xor butterfly (offsets 4, 2, 1): bit-identical to the tile kernels
@@ -89,6 +103,37 @@ __device__ __forceinline__ void store8(double* dst, const double (&v)[8], bool v
 #pragma unroll
     for (int j = 0; j < 8; j++) dst[j] = v[j];
   }
+}
+
+// E doubles of one problem to global memory (E = 8: two 256-bit stores, 4: one, 2: one 128-bit store)
+template <int E>
+__device__ __forceinline__ void storeE(double* dst, const double (&v)[E], bool vec32) {
+  if constexpr (E == 2) {
+    if (vec32) {
+      asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(dst), "d"(v[0]), "d"(v[1]) : "memory");
+    } else {
+      dst[0] = v[0];
+      dst[1] = v[1];
+    }
+  } else {
+    if (vec32) {
+#pragma unroll
+      for (int j = 0; j < E; j += 4)
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "d"(v[j]), "d"(v[j + 1]), "d"(v[j + 2]), "d"(v[j + 3])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < E; j++) dst[j] = v[j];
+    }
+  }
+}
+
+// the in-thread stages (offsets E/2 .. 1) of tile_sum<8>'s butterfly over the E elements a lane holds
+template <int E>
+__device__ __forceinline__ double sum_local(const double (&v)[E]) {
+  if constexpr (E == 8) return sum8(v);
+  else if constexpr (E == 4) return __dadd_rn(__dadd_rn(v[0], v[2]), __dadd_rn(v[1], v[3]));
+  else return __dadd_rn(v[0], v[1]);
 }
 
 // Branch-free sqrt / reciprocal: the fast paths of CUDA's own IEEE sqrt() and 1/x, instruction for instruction (MUFU seed,
@@ -133,7 +178,7 @@ __device__ __forceinline__ unsigned long long tpp_now() {
 }
 #define TPP_MARK(k, v)                                                                      \
   do {                                                                                      \
-    if (g_tpp_trace != nullptr && lane == 0) g_tpp_trace[((size_t)blockIdx.x * TPP_WARPS + warp) * 16 + (k)] = (v); \
+    if (g_tpp_trace != nullptr && lane == 0) g_tpp_trace[((size_t)blockIdx.x * TPP_WARPS + warp) * 32 + (k)] = (v); \
   } while (0)
 #else
 #define TPP_MARK(k, v) \
@@ -141,12 +186,26 @@ __device__ __forceinline__ unsigned long long tpp_now() {
   } while (0)
 #define tpp_now() 0ULL
 #endif
+#ifdef DQ_TPP_TRACE
+#define TPP_CLK(v) const long long v = clock64()
+#define TPP_ACC(a, t1, t0) a += (unsigned long long)((t1) - (t0))
+#else
+#define TPP_CLK(v) \
+  do {             \
+  } while (0)
+#define TPP_ACC(a, t1, t0) \
+  do {                     \
+  } while (0)
+#endif
 
-template <int PROX>
-__global__ void __launch_bounds__(TPP_THREADS, DQ_TPP_CTAS) admm_fwd_tpp8_kernel(const FwdParams p, const int cap_it) {
-  using R = TppRec<PROX>;
+template <int PROX, int E>
+__global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_kernel(const FwdParams p, const int cap_it) {
+  using R = TppRec<PROX, E>;
+  using G = TppGeo<E>;
   constexpr bool QCQP = (PROX == PROX_DISK);
-  constexpr int T = 8;
+  constexpr int T = 8;               // lanes per problem in the tile phase
+  constexpr int TPP_CAP = G::CAP;
+  constexpr int LT = G::T;           // lanes per problem in the main loop
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* recs = reinterpret_cast<double*>(smem_raw);
   double* sdump = recs + TPP_CAP * R::D;                                 // [STRAG][SD] parked (l_2, u, q_prox)
@@ -167,7 +226,7 @@ __global__ void __launch_bounds__(TPP_THREADS, DQ_TPP_CTAS) admm_fwd_tpp8_kernel
 
   TPP_MARK(0, tpp_now());
   if (tid == 0) {
-    ctl[0] = nb < TPP_THREADS ? nb : TPP_THREADS;  // the first queue positions go to the threads directly
+    ctl[0] = nb < G::SLOTS ? nb : G::SLOTS;  // the first queue positions go to the slots directly
     ctl[1] = 0;
     ctl[2] = 0;
   }
@@ -345,10 +404,17 @@ __global__ void __launch_bounds__(TPP_THREADS, DQ_TPP_CTAS) admm_fwd_tpp8_kernel
   __syncthreads();
   TPP_MARK(4, tpp_now());
 
-  // ---- 3. the ADMM loop (Solver.cpp:79-121 / :538-580), one problem per thread
+  // ---- 3. the ADMM loop (Solver.cpp:79-121 / :538-580): a slot of LT = 8 / E adjacent lanes per problem, lane h of a slot
+  // holding elements E h .. E h + E - 1.  Everything per-problem (residual maxima, decisions, rho, counters) is computed by
+  // every lane of the slot with identical bits, so control flow is slot-uniform.
   {
-    double q[8], pinv[8], l2[8], u[8], qp[8];
-    double rad[QCQP ? 4 : 1];
+    const int h = lane & (LT - 1);
+    const int eo = E * h;                    // this lane's first element
+    const int slot_lane = lane & ~(LT - 1);  // first lane of this lane's slot
+    const bool leader = h == 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    double q[E], pinv[E], l2[E], u[E], qp[E];
+    double rad[QCQP ? E / 2 : 1];
     double rho = 1.0, irho = 1.0;
     int it = 0, cpt5 = 0, rho_up = 0, ridx = 0;
     bool live = false;
@@ -357,14 +423,14 @@ __global__ void __launch_bounds__(TPP_THREADS, DQ_TPP_CTAS) admm_fwd_tpp8_kernel
       ridx = order[pos];
       rec = recs + ridx * R::D;
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        q[i] = rec[R::Q + i];
-        pinv[i] = rec[R::PINV + i];
+      for (int i = 0; i < E; i++) {
+        q[i] = rec[R::Q + eo + i];
+        pinv[i] = rec[R::PINV + eo + i];
         l2[i] = 0.0; u[i] = 0.0; qp[i] = q[i];  // l_2 = u = 0, q_prox = q   :67-74
       }
       if (QCQP) {
 #pragma unroll
-        for (int c = 0; c < (QCQP ? 4 : 1); c++) rad[c] = rec[R::X0 + c];
+        for (int c = 0; c < (QCQP ? E / 2 : 1); c++) rad[c] = rec[R::X0 + eo / 2 + c];
       }
       rho = rec[R::RHO];
       irho = rec[R::IRHO];
@@ -372,46 +438,79 @@ __global__ void __launch_bounds__(TPP_THREADS, DQ_TPP_CTAS) admm_fwd_tpp8_kernel
       live = true;
     };
 #pragma unroll
-    for (int i = 0; i < 8; i++) q[i] = pinv[i] = l2[i] = u[i] = qp[i] = 0.0;
+    for (int i = 0; i < E; i++) q[i] = pinv[i] = l2[i] = u[i] = qp[i] = 0.0;
     rad[0] = 0.0;
 #ifndef DQ_TPP_REFILL
 #define DQ_TPP_REFILL 2  // power of two
 #endif
     bool done = true;  // nothing more to take from the queue
-    if (tid < nb) {
-      take(tid);
+    if (tid / LT < nb) {
+      take(tid / LT);
       done = false;
     }
     unsigned ntrips = 0;
+#ifdef DQ_TPP_TRACE
+    unsigned long long acc_body = 0, acc_dec = 0, acc_upd = 0, acc_fin = 0, acc_refill = 0, acc_u1 = 0, acc_u2 = 0, acc_u3 = 0;
+#endif
+
+    int* ul = ulist + warp * 32;  // problems posted for a rho update in the current trip
+    // one posted item: e < 8 diagonal entry (m += c, then (1/s)(1/s), s = sqrt(m): LLT of a diagonal matrix and the two
+    // substitutions against I), e == 8: 1 / rho, e == 9: 1 / (tau_dec after its next decay)
+    auto item_load = [&](int item, int nit, double*& r, int& e, bool& v) -> double {
+      v = item < nit;
+      const int sidx = item / 10;
+      e = item - 10 * sidx;
+      r = recs + (v ? ul[sidx] : 0) * R::D;
+      const double x0 = r[e < 8 ? R::M + e : (e == 8 ? R::RHO : R::TDK)];
+      const double xs = __dadd_rn(x0, r[R::CADD]);  // P += c I
+      const double xin = v ? (e < 8 ? xs : x0) : 1.0;
+      if (v && e < 8) r[R::M + e] = xin;
+      return xin;
+    };
+    auto item_store = [&](double* r, int e, bool v, double xin, double a) {
+#ifndef DQ_TPP_NOSLOW
+      if (!fast_ok(xin)) a = 1.0 / (e < 8 ? sqrt(xin) : xin);  // exponent near the ends of the double range: the library's
+#endif
+      if (v) r[e < 8 ? R::PINV + e : (e == 8 ? R::IRHO : R::ITDK)] = e < 8 ? __dmul_rn(a, a) : a;
+    };
 
     while (__any_sync(FULL_MASK, live || !done)) {
       ++ntrips;
-      // ---- one iteration of every live lane's problem
-      unsigned long long adl[8], adu[8];  // |l_2 - l_2_pred|, |l_2 - (alpha l + (1-alpha) l_2_pred)| as bit patterns
-      double lsq[8];
+      TPP_CLK(c0);
+      // ---- one iteration of every slot's problem (idle slots compute on stale registers and discard)
+      unsigned long long adl[E], adu[E];  // |l_2 - l_2_pred|, |l_2 - (alpha l + (1-alpha) l_2_pred)| as bit patterns
+      double lsq[E];
       auto elem = [&](int i, double& z, double& relax) {
         const double rhs = __dsub_rn(__dsub_rn(__dmul_rn(rho, l2[i]), u[i]), qp[i]);  // l = Pinv (rho l_2 - u - q_prox)  :80
         const double l = __dmul_rn(pinv[i], rhs);
-        qp[i] = __dsub_rn(q[i], __dmul_rn(mu, l));                                    // :81
+        const double t = __dmul_rn(mu, l);
+        qp[i] = __dsub_rn(q[i], t);                                                   // :81
         relax = __fma_rn(-0.5, l2[i], __dmul_rn(1.5, l));  // alpha l + (1-alpha) l_2_pred: -0.5 l_2 is exact, so this FMA rounds once, like the sum
         z = __dadd_rn(relax, div_by(u[i], rho, irho));                                // :82   ... + u/rho
         if (QCQP) lsq[i] = __dmul_rn(l, l);
       };
       auto finish = [&](int i, double l2n, double relax) {
         const double du = __dsub_rn(relax, l2n);      // :86 up to sign
-        u[i] = __dadd_rn(u[i], __dmul_rn(rho, du));   // :83
+        const double t = __dmul_rn(rho, du);
+        u[i] = __dadd_rn(u[i], t);                    // :83
         const double dl = __dsub_rn(l2n, l2[i]);      // :84
         l2[i] = l2n;
         adl[i] = abs_bits(dl);
         adu[i] = abs_bits(du);
       };
-      auto max8 = [](const unsigned long long (&v)[8]) {  // non-negative doubles order like their bit patterns
+      auto maxE = [](const unsigned long long (&v)[E]) {  // non-negative doubles order like their bit patterns
         auto mx = [](unsigned long long a, unsigned long long b) { return a > b ? a : b; };
-        return mx(mx(mx(v[0], v[1]), mx(v[2], v[3])), mx(mx(v[4], v[5]), mx(v[6], v[7])));
-      };
-      if constexpr (QCQP) {  // prox_circle :505-519, one contact = two elements of this thread
+        unsigned long long m;
+        if constexpr (E == 8) m = mx(mx(mx(v[0], v[1]), mx(v[2], v[3])), mx(mx(v[4], v[5]), mx(v[6], v[7])));
+        else if constexpr (E == 4) m = mx(mx(v[0], v[1]), mx(v[2], v[3]));
+        else m = mx(v[0], v[1]);
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int o = 1; o < LT; o <<= 1) m = mx(m, __shfl_xor_sync(FULL_MASK, m, o));  // the other lanes of the slot
+        return m;
+      };
+      if constexpr (QCQP) {  // prox_circle :505-519, one contact = two elements of this lane
+#pragma unroll
+        for (int c = 0; c < E / 2; c++) {
           double z0, z1, r0, r1;
           elem(2 * c, z0, r0);
           elem(2 * c + 1, z1, r1);
@@ -424,18 +523,18 @@ __global__ void __launch_bounds__(TPP_THREADS, DQ_TPP_CTAS) admm_fwd_tpp8_kernel
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < E; i++) {
           double z, relax;
           elem(i, z, relax);
           double l2n;
           if (PROX == PROX_NONNEG) {
             l2n = z < 0 ? 0.0 : z;  // cwiseMax(0)
           } else {                  // solveBoxQP :219-220 / solveSignedBoxQP :396-398
-            const double lo = rec[R::X0 + i], hi = rec[R::X1 + i];
+            const double lo = rec[R::X0 + eo + i], hi = rec[R::X1 + eo + i];
             l2n = z < lo ? lo : z;
             l2n = hi < l2n ? hi : l2n;
             if (PROX == PROX_SIGNED_BOX) {
-              const double vs = rec[R::X2 + i];
+              const double vs = rec[R::X2 + eo + i];
               double w = __dmul_rn(vs, l2n);
               w = 0 < w ? 0.0 : w;
               l2n = __dmul_rn(vs, w);
@@ -445,12 +544,18 @@ __global__ void __launch_bounds__(TPP_THREADS, DQ_TPP_CTAS) admm_fwd_tpp8_kernel
         }
       }
       ++it;
+      TPP_CLK(c1);
       // ---- decisions (see admm_loop: fl(c x) is monotone, so the reference's comparisons of maxima are these)
-      const double amax = __longlong_as_double((long long)max8(adl)), pmax = __longlong_as_double((long long)max8(adu));
+      const double amax = __longlong_as_double((long long)maxE(adl)), pmax = __longlong_as_double((long long)maxE(adu));
       const double rd = __dmul_rn(rho, amax);
       bool stop = rd < eps;  // :88 / :548
       if (QCQP) {            // ... and res_prim < eps + eps_rel |l|_2
-        const double thr = __dadd_rn(eps, __dmul_rn(1e-4, sqrt(sum8(lsq))));
+#pragma unroll
+        for (int o = LT / 2; o > 0; o >>= 1) {  // the cross-lane stages of tile_sum<8>'s butterfly come first (offsets 4, 2)
+#pragma unroll
+          for (int i = 0; i < E; i++) lsq[i] = __dadd_rn(lsq[i], __shfl_xor_sync(FULL_MASK, lsq[i], o));
+        }
+        const double thr = __dadd_rn(eps, __dmul_rn(1e-4, sqrt(sum_local<E>(lsq))));
         stop = stop && (pmax < thr);
       }
       const bool inc = pmax > __dmul_rn(10., rd);  // :92 / :552
@@ -460,167 +565,116 @@ __global__ void __launch_bounds__(TPP_THREADS, DQ_TPP_CTAS) admm_fwd_tpp8_kernel
       const bool need = cnt && cpt5 == 0;  // at most one rho update per 5 counted iterations  :93 / :553
       if (cnt) cpt5 = (cpt5 == 4) ? 0 : cpt5 + 1;
 
-      // ---- adaptive rho :91-120 / :551-579.  Scalar part per lane -- every reciprocal it needs was computed ahead of time
-      // (1/tau_dec, and 1/tau_dec' for the tau_dec' a decay would give) -- then the whole warp shares the reciprocals the
-      // posted problems need next: (P + c I)^-1 element by element, 1/rho, and 1/(the next decayed tau_dec); two
-      // independent chains per lane.
-#ifndef DQ_TPP_COOP
-#define DQ_TPP_COOP 0
-#endif
-      const unsigned um = __ballot_sync(FULL_MASK, need);
+      // ---- adaptive rho :91-120 / :551-579.  The scalar part (tau decay, new rho, the increment c of the diagonal) is
+      // branch-free -- every reciprocal it needs was computed ahead of time: 1/tau_dec, and 1/tau_dec' for the tau_dec' a decay
+      // would give -- and executed by the whole warp when any slot needs an update (nearly every trip); the slots that do
+      // post their problem in the warp's list.  Then ALL 32 lanes share the reciprocals the posted problems need next:
+      // (P + c I)^-1 element by element, 1/rho, 1/(tau_dec after its next decay), two independent chains per lane and round.
+      const unsigned um = __ballot_sync(FULL_MASK, need) & G::LEADERS;
+      TPP_CLK(c2);
       if (um) {
-        int* ul = ulist + warp * 32;
+        const double tau_inc = rec[R::TAUI], tau_dec = rec[R::TAUD], itd = rec[R::ITD], tdk = rec[R::TDK], itdk = rec[R::ITDK];
+        const bool rev = inc ? (rho_up == -1) : (rho_up == 1);  // direction reversal: the taus decay  :94-97 / :108-111
+        const bool dk_i = rev && (!QCQP || inc), dk_d = rev && (!QCQP || !inc);  // the QP decays both, the QCQP only the one it uses
+        const double n_ti = dk_i ? __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1))) : tau_inc;
+        const double n_td = dk_d ? tdk : tau_dec, n_itd = dk_d ? itdk : itd;
+        const double n_tdk = dk_d ? __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tdk, 1))) : tdk;
+        const double c = __dmul_rn(rho, __dsub_rn(inc ? n_ti : n_itd, 1));               // :98 / :557, :112 / :571
+        const double n_rho = inc ? __dmul_rn(rho, n_ti) : div_by(rho, n_td, n_itd);     // rho *= tau_inc | rho /= tau_dec
         if (need) {
-          double tau_inc = rec[R::TAUI], tau_dec = rec[R::TAUD], itd = rec[R::ITD], c;
-          const bool rev = inc ? (rho_up == -1) : (rho_up == 1);  // direction reversal: the taus decay  :94-97 / :108-111
-          if (rev) {
-            if (!QCQP || inc) tau_inc = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1)));  // the QP decays both, the QCQP
-            if (!QCQP || !inc) {                                                              // only the one it uses
-              tau_dec = rec[R::TDK];
-              itd = rec[R::ITDK];
-              rec[R::TAUD] = tau_dec;
-              rec[R::ITD] = itd;
-              rec[R::TDK] = __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_dec, 1)));
-            }
-            rec[R::TAUI] = tau_inc;
-          }
-          if (inc) {
-            c = __dmul_rn(rho, __dsub_rn(tau_inc, 1));  // :98 / :557
-            rho = __dmul_rn(rho, tau_inc);
-            rho_up = 1;
-          } else {
-            c = __dmul_rn(rho, __dsub_rn(itd, 1));  // :112 / :571
-            rho = div_by(rho, tau_dec, itd);        // rho /= tau_dec
-            rho_up = -1;
-          }
-          rec[R::RHO] = rho;
-          if (DQ_TPP_COOP) {
+          rho = n_rho;
+          rho_up = inc ? 1 : -1;
+          if (leader) {
+            rec[R::TAUI] = n_ti;
+            rec[R::TAUD] = n_td;
+            rec[R::ITD] = n_itd;
+            rec[R::TDK] = n_tdk;
+            rec[R::RHO] = n_rho;
             rec[R::CADD] = c;
-            ul[__popc(um & ((1u << lane) - 1u))] = ridx;
-          } else {  // lane-local: eight independent chains interleave; more FP64 work than the shared version, far less latency
-            double m8[8];
-            const double tdk = rec[R::TDK];
-            bool ok = fast_ok(rho) && fast_ok(tdk);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              m8[i] = __dadd_rn(rec[R::M + i], c);  // P += c I
-              rec[R::M + i] = m8[i];
-              ok = ok && fast_ok(m8[i]);
-            }
-            if (ok) {
-#pragma unroll
-              for (int i = 0; i < 8; i++) {
-                const double a = fast_rcp(fast_sqrt(m8[i]));
-                pinv[i] = __dmul_rn(a, a);
-              }
-              irho = fast_rcp(rho);
-              if (rev) rec[R::ITDK] = fast_rcp(tdk);
-            } else {
-              for (int i = 0; i < 8; i++) {
-                const double a = 1.0 / sqrt(rec[R::M + i]);
-                rec[R::PINV + i] = __dmul_rn(a, a);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; i++) pinv[i] = rec[R::PINV + i];
-              irho = 1.0 / rho;
-              if (rev) rec[R::ITDK] = 1.0 / tdk;
-            }
-            rec[R::IRHO] = irho;
-#pragma unroll
-            for (int i = 0; i < 8; i++) rec[R::PINV + i] = pinv[i];  // the record stays current (park / tile phase read it)
+            ul[__popc(um & lt_mask)] = ridx;
           }
-        }
-        if (DQ_TPP_COOP) {
-        __syncwarp();
-        const int nitems = __popc(um) * 10;  // per posted problem: eight diagonal entries, 1 / rho, 1 / (tau_dec after its next decay)
-        for (int base = 0; base < nitems; base += 64) {
-          double xin[2];
-          double* r[2];
-          int e[2];
-          bool v[2];
-          bool ok = true;
-#pragma unroll
-          for (int k = 0; k < 2; k++) {
-            const int item = base + 32 * k + lane;
-            v[k] = item < nitems;
-            const int sidx = item / 10;
-            e[k] = item - 10 * sidx;
-            r[k] = recs;
-            xin[k] = 1.0;
-            if (v[k]) {
-              r[k] = recs + ul[sidx] * R::D;
-              if (e[k] < 8) {  // P += c I
-                xin[k] = __dadd_rn(r[k][R::M + e[k]], r[k][R::CADD]);
-                r[k][R::M + e[k]] = xin[k];
-              } else {
-                xin[k] = r[k][e[k] == 8 ? R::RHO : R::TDK];
-              }
-            }
-            ok = ok && fast_ok(xin[k]);
-          }
-          double a[2];
-          if (__all_sync(FULL_MASK, ok)) {  // LLT of a diagonal matrix and two substitutions against I: (1/s)(1/s), s = sqrt(m)
-#pragma unroll
-            for (int k = 0; k < 2; k++) a[k] = fast_rcp(e[k] < 8 ? fast_sqrt(xin[k]) : xin[k]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 2; k++) a[k] = 1.0 / (e[k] < 8 ? sqrt(xin[k]) : xin[k]);
-          }
-#pragma unroll
-          for (int k = 0; k < 2; k++)
-            if (v[k]) r[k][e[k] < 8 ? R::PINV + e[k] : (e[k] == 8 ? R::IRHO : R::ITDK)] = e[k] < 8 ? __dmul_rn(a[k], a[k]) : a[k];
         }
         __syncwarp();
-        if (need) {
+        TPP_CLK(u1);
+        TPP_ACC(acc_u1, u1, c2);
+        {
+          const int nis = __popc(um) * 10;
+          for (int base = 0; base < nis; base += 64) {
+            double* r0; double* r1; int e0, e1; bool v0, v1;
+            const double x0 = item_load(base + lane, nis, r0, e0, v0), x1 = item_load(base + 32 + lane, nis, r1, e1, v1);
+            const double s0 = fast_sqrt(x0), s1 = fast_sqrt(x1);  // (computed for the two reciprocal-only items too: no branch, the chains interleave)
+            const double a0 = fast_rcp(e0 < 8 ? s0 : x0), a1 = fast_rcp(e1 < 8 ? s1 : x1);
+            item_store(r0, e0, v0, x0, a0);
+            item_store(r1, e1, v1, x1, a1);
+          }
+          TPP_CLK(u2);
+          TPP_ACC(acc_u2, u2, u1);
+          __syncwarp();
+          if (need) {
 #pragma unroll
-          for (int i = 0; i < 8; i++) pinv[i] = rec[R::PINV + i];
-          irho = rec[R::IRHO];
-        }
+            for (int i = 0; i < E; i++) pinv[i] = rec[R::PINV + eo + i];
+            irho = rec[R::IRHO];
+          }
+          TPP_CLK(u3);
+          TPP_ACC(acc_u3, u3, u2);
         }
       }
 
-      // ---- finished problems leave (x* = l_2, :122 / :581), long runners are parked for the tile phase; both refill
-      bool park = live && !fin && it == cap_it;
-      if (park) {
-        const int slot = atomicAdd(&ctl[2], 1);
-        if (slot < TPP_STRAG) {
-          double* sd = sdump + slot * TPP_SD;
+      TPP_CLK(c3);
+      // ---- finished problems leave (x* = l_2, :122 / :581), long runners are parked for the tile phase
+      bool park = live && !fin && cap_it > 0 && it >= cap_it;
+      const unsigned pm = __ballot_sync(FULL_MASK, park);
+      if (pm) {  // rare
+        int sl = 0;
+        if (park && leader) sl = atomicAdd(&ctl[2], 1);
+        sl = __shfl_sync(FULL_MASK, sl, slot_lane);
+        if (park) {
+          if (sl < TPP_STRAG) {
+            double* sd = sdump + sl * TPP_SD + eo;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            sd[i] = l2[i];
-            sd[8 + i] = u[i];
-            sd[16 + i] = qp[i];
+            for (int i = 0; i < E; i++) {
+              sd[i] = l2[i];
+              sd[8 + i] = u[i];
+              sd[16 + i] = qp[i];
+            }
+            if (leader) {
+              sinfo[4 * sl] = ridx;
+              sinfo[4 * sl + 1] = it;
+              sinfo[4 * sl + 2] = cpt5;
+              sinfo[4 * sl + 3] = rho_up;
+            }
+          } else {
+            park = false;  // no room: it simply goes on here
           }
-          sinfo[4 * slot] = ridx;
-          sinfo[4 * slot + 1] = it;
-          sinfo[4 * slot + 2] = cpt5;
-          sinfo[4 * slot + 3] = rho_up;
-        } else {
-          park = false;  // no room: it simply goes on here
         }
       }
       if (fin) {
         const long long prob = b0 + ridx;
-        store8(p.x + prob * 8, l2, xvec);
-        if (p.iters) p.iters[prob] = it;
+        storeE<E>(p.x + prob * 8 + eo, l2, xvec);
+        if (leader && p.iters) p.iters[prob] = it;
       }
       if (fin || park) live = false;
-      // refill: an idle lane takes the next problem of the queue -- on every DQ_TPP_REFILL-th trip only (the section costs
-      // ~70 instructions and two shared-memory round trips whenever any lane of the warp is idle, i.e. on most trips)
+      TPP_CLK(c4);
+      // refill: an idle slot takes the next problem of the queue -- on every DQ_TPP_REFILL-th trip only (the section costs
+      // ~70 instructions and two shared-memory round trips whenever any slot of the warp is idle, i.e. on most trips)
       if ((ntrips & (DQ_TPP_REFILL - 1)) == 0) {
-        const unsigned dm = __ballot_sync(FULL_MASK, !live && !done);
+        const unsigned dm = __ballot_sync(FULL_MASK, !live && !done) & G::LEADERS;
         if (dm) {
           int base = 0;
           if (lane == 0) base = atomicAdd(&ctl[0], __popc(dm));
           base = __shfl_sync(FULL_MASK, base, 0);
+          const int pos = base + __popc(dm & ((1u << slot_lane) - 1u));  // slot-uniform
           if (!live && !done) {
-            const int pos = base + __popc(dm & ((1u << lane) - 1u));
             if (pos < nb) take(pos);
             else done = true;  // the queue is empty
           }
         }
       }
+      TPP_CLK(c5);
+      TPP_ACC(acc_body, c1, c0); TPP_ACC(acc_dec, c2, c1); TPP_ACC(acc_upd, c3, c2); TPP_ACC(acc_fin, c4, c3); TPP_ACC(acc_refill, c5, c4);
     }
+    TPP_MARK(16, acc_u1); TPP_MARK(17, acc_u2); TPP_MARK(18, acc_u3);
+    TPP_MARK(10, acc_body); TPP_MARK(11, acc_dec); TPP_MARK(12, acc_upd); TPP_MARK(13, acc_fin); TPP_MARK(14, acc_refill);
     TPP_MARK(5, tpp_now());
     TPP_MARK(8, (unsigned long long)ntrips);
   }
@@ -832,7 +886,14 @@ int set_tpp_cap_it(int v) {
   return old;
 }
 
-template <int PROX>
+static int g_tpp_elems = 8;  // elements per lane: 8 or 4 (dq_set_forward_tuning key 2)
+int set_tpp_elems(int e) {
+  const int old = g_tpp_elems;
+  if (e == 8 || e == 4) g_tpp_elems = e;
+  return old;
+}
+
+template <int PROX, int E>
 static cudaError_t launch_tpp8_t(const FwdParams& p, cudaStream_t stream) {
   static int sm_count[64] = {0};  // per device; a benign race writes the same value
   int dev = 0;
@@ -843,27 +904,35 @@ static cudaError_t launch_tpp8_t(const FwdParams& p, cudaStream_t stream) {
     int sms = 0;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(admm_fwd_tpp8_kernel<PROX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TppRec<PROX>::bytes);
+    e = cudaFuncSetAttribute(admm_fwd_tpp8_kernel<PROX, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TppRec<PROX, E>::bytes);
     if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(admm_fwd_tpp8_kernel<PROX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(admm_fwd_tpp8_kernel<PROX, E>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (sms < 1) return cudaErrorLaunchOutOfResources;
     sm_count[dev] = sms;
   }
-  const long long sms = sm_count[dev];
-  const long long k = (p.B + sms * TPP_CAP - 1) / (sms * TPP_CAP);
+  const long long sms = sm_count[dev], cap = TppGeo<E>::CAP;
+  const long long k = (p.B + sms * cap - 1) / (sms * cap);
   long long grid = sms * k;
   if (grid > p.B) grid = p.B;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  admm_fwd_tpp8_kernel<PROX><<<(unsigned)grid, TPP_THREADS, TppRec<PROX>::bytes, stream>>>(p, g_tpp_cap_it);
+  admm_fwd_tpp8_kernel<PROX, E><<<(unsigned)grid, TPP_THREADS, TppRec<PROX, E>::bytes, stream>>>(p, g_tpp_cap_it);
   return cudaGetLastError();
+}
+
+template <int PROX>
+static cudaError_t launch_tpp8_p(const FwdParams& p, cudaStream_t stream) {
+  switch (g_tpp_elems) {
+    case 4: return launch_tpp8_t<PROX, 4>(p, stream);
+    default: return launch_tpp8_t<PROX, 8>(p, stream);
+  }
 }
 
 cudaError_t launch_tpp8(const FwdParams& p, int prox, cudaStream_t stream) {
   switch (prox) {
-    case PROX_NONNEG: return launch_tpp8_t<PROX_NONNEG>(p, stream);
-    case PROX_DISK: return launch_tpp8_t<PROX_DISK>(p, stream);
-    case PROX_BOX: return launch_tpp8_t<PROX_BOX>(p, stream);
-    default: return launch_tpp8_t<PROX_SIGNED_BOX>(p, stream);
+    case PROX_NONNEG: return launch_tpp8_p<PROX_NONNEG>(p, stream);
+    case PROX_DISK: return launch_tpp8_p<PROX_DISK>(p, stream);
+    case PROX_BOX: return launch_tpp8_p<PROX_BOX>(p, stream);
+    default: return launch_tpp8_p<PROX_SIGNED_BOX>(p, stream);
   }
 }
 

@@ -371,6 +371,7 @@ int64_t dq_set_forward_tuning(int32_t key, int64_t value) {
   switch (key) {
     case 0: return dq::set_tpp_cap_it((int)value);
     case 1: return dq::set_tpp_min_batch(value);
+    case 2: return dq::set_tpp_elems((int)value);
     default: return -1;
   }
 }
@@ -441,18 +442,26 @@ int dq_boxqp_forward(const double* P, const double* q, const double* l_min, cons
 int dq_boxqp_backward(const double* P, const double* q, const double* l_min, const double* l_max, const double* x,
                       const double* grad_x, double* grad_P, double* grad_q, double* grad_l_min, double* grad_l_max,
                       int64_t B, int32_t N, void* stream) {
+  return dq_boxqp_backward_ex(P, q, l_min, l_max, x, grad_x, grad_P, grad_q, grad_l_min, grad_l_max, nullptr, nullptr, B, N,
+                              stream);
+}
+
+int dq_boxqp_backward_ex(const double* P, const double* q, const double* l_min, const double* l_max, const double* x,
+                         const double* grad_x, double* grad_P, double* grad_q, double* grad_l_min, double* grad_l_max,
+                         double* gamma, double* dgamma, int64_t B, int32_t N, void* stream) {
   int rc = check_common(P, q, x, B, N);
   if (rc != DQ_OK) return rc;
   if (B > 0 && (!grad_x || !l_min || !l_max)) return DQ_ERR_BAD_ARG;
   if (!aligned8(grad_x) || !aligned8(l_min) || !aligned8(l_max) || !aligned8(grad_P) || !aligned8(grad_q) ||
-      !aligned8(grad_l_min) || !aligned8(grad_l_max))
+      !aligned8(grad_l_min) || !aligned8(grad_l_max) || !aligned8(gamma) || !aligned8(dgamma))
     return DQ_ERR_ALIGN;
-  if (B == 0 || (!grad_P && !grad_q && !grad_l_min && !grad_l_max)) return DQ_OK;
+  if (B == 0 || (!grad_P && !grad_q && !grad_l_min && !grad_l_max && !gamma && !dgamma)) return DQ_OK;
   const int T = dq::tile_width(N);
   const int G = 32 / T;
   dq::BoxBwdParams p;
   p.P = P; p.q = q; p.l_min = l_min; p.l_max = l_max; p.x = x; p.grad_x = grad_x;
   p.grad_P = grad_P; p.grad_q = grad_q; p.grad_l_min = grad_l_min; p.grad_l_max = grad_l_max;
+  p.gamma = gamma; p.dgamma = dgamma;
   p.B = B; p.N = N;
   p.n_groups = (B + G - 1) / G;
   cudaError_t e = dq::launch_boxqp_bwd(p, T, (cudaStream_t)stream);

@@ -287,6 +287,14 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
     if (p.grad_q) p.grad_q[prob * N + ti] = -dl;                       // qcqp.py:88
     if (p.grad_l_min) p.grad_l_min[prob * N + ti] = -(dg_lo * gam_lo);  // qcqp.py:91
     if (p.grad_l_max) p.grad_l_max[prob * N + ti] = dg_up * gam_up;     // qcqp.py:93 with the sign of d(l_max) fixed
+    if (p.gamma) {  // dualFromPrimalBoxQP's gamma (2N): [lower bounds ; upper bounds]   pybindings.cpp:42
+      p.gamma[prob * 2 * N + ti] = gam_lo;
+      p.gamma[prob * 2 * N + N + ti] = gam_up;
+    }
+    if (p.dgamma) {  // blgamma[:2N] of solveDerivativesBoxQP   :359-361
+      p.dgamma[prob * 2 * N + ti] = dg_lo;
+      p.dgamma[prob * 2 * N + N + ti] = dg_up;
+    }
   }
   if (p.grad_P) {  // qcqp.py:86  grad_P = -dl l^T : lane ti writes row ti
     xb[ti] = li;

@@ -6,8 +6,10 @@
 * the unbatched autograd functions of ``qcqp_no_batch.py`` (:23-108): ``QPFn2`` / ``QCQPFn2`` on ``P (N,N)``,
   ``q (N,1)``, ``l_n, mu (N/2,1)``.
 
-The root-level ``diffqcqp.py`` and ``qcqp_no_batch.py`` re-export these so the reference's import lines keep
-working.  The Box / SignedBox functions of the module are outside this repo's scope and raise.
+* the Box / SignedBox functions of the same module -- ``solveBoxQP``, ``solveSignedBoxQP``, ``solveDerivativesBoxQP``
+  (pybindings.cpp:32-52,77-81) -- likewise.
+
+The root-level ``diffqcqp.py`` and ``qcqp_no_batch.py`` re-export these so the reference's import lines keep working.
 One kernel launch per call: this surface exists for compatibility, the batched one in ``qcqp.py`` for speed.
 """
 from __future__ import annotations
@@ -85,16 +87,42 @@ def solveDerivativesQCQP(P, q, l_n, mu, l, grad_l, epsilon=1e-10):
     return E1, E2, blgamma
 
 
-def _out_of_scope(name):
-    def f(*a, **k):
-        raise NotImplementedError(f"{name} is outside the QP/QCQP hot path this package replaces (DESIGN.md section 9)")
-    f.__name__ = name
-    return f
+def solveBoxQP(P, q, l_min, l_max, warm_start, epsilon=1e-10, mu_prox=1e-7, max_iter=1000, adaptative_rho=True):
+    """pybindings.cpp:32-37,77 -> (N,) array."""
+    n = np.asarray(q).size
+    x = _b.boxqp_forward(_t(P, (1, n, n)), _t(q, (1, n, 1)), _t(l_min, (1, n, 1)), _t(l_max, (1, n, 1)), epsilon, max_iter,
+                         mu_prox, adaptative_rho)
+    return x.reshape(n).cpu().numpy()
 
 
-solveBoxQP = _out_of_scope("solveBoxQP")
-solveSignedBoxQP = _out_of_scope("solveSignedBoxQP")
-solveDerivativesBoxQP = _out_of_scope("solveDerivativesBoxQP")
+def solveSignedBoxQP(P, q, l_min, l_max, v, warm_start, epsilon=1e-10, mu_prox=1e-7, max_iter=1000, adaptative_rho=True):
+    """pybindings.cpp:47-52,78 -> (N,) array."""
+    n = np.asarray(q).size
+    x = _b.boxqp_forward(_t(P, (1, n, n)), _t(q, (1, n, 1)), _t(l_min, (1, n, 1)), _t(l_max, (1, n, 1)), epsilon, max_iter,
+                         mu_prox, adaptative_rho, v=_t(v, (1, n, 1)))
+    return x.reshape(n).cpu().numpy()
+
+
+def solveDerivativesBoxQP(P, q, l_min, l_max, l, grad_l, epsilon=1e-10):
+    """pybindings.cpp:39-45,81 -> (blgamma (3N,), gamma (2N,)): blgamma = [dgamma_lower ; dgamma_upper ; dl]."""
+    if epsilon != 1e-10:
+        raise ValueError("the backward kernels implement the binding's default epsilon=1e-10 only")
+    n = np.asarray(q).size
+    dev = _dev()
+    Pd, qd = _t(P, (1, n, n)), _t(q, (1, n, 1))
+    lo, hi = _t(l_min, (1, n, 1)), _t(l_max, (1, n, 1))
+    xd, gd = _t(l, (1, n, 1)), _t(grad_l, (1, n, 1))
+    gq = torch.empty((1, n, 1), dtype=torch.float64, device=dev)
+    gam = torch.empty((1, 2 * n), dtype=torch.float64, device=dev)
+    dgam = torch.empty((1, 2 * n), dtype=torch.float64, device=dev)
+    L = _lib.load()
+    with torch.cuda.device(dev):
+        rc = L.dq_boxqp_backward_ex(Pd.data_ptr(), qd.data_ptr(), lo.data_ptr(), hi.data_ptr(), xd.data_ptr(), gd.data_ptr(),
+                                    None, gq.data_ptr(), None, None, gam.data_ptr(), dgam.data_ptr(), 1, n,
+                                    torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "dq_boxqp_backward_ex")
+    blgamma = np.concatenate([dgam.reshape(2 * n).cpu().numpy(), (-gq).reshape(n).cpu().numpy()])  # grad_q = -dl
+    return blgamma, gam.reshape(2 * n).cpu().numpy()
 
 
 class QPFn2(Function):

@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -101,10 +102,16 @@ def _compute_device(*tensors) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+MAX_N = 32  # DQ_MAX_N of include/diffqcqp_b200.h (dq_max_n())
+
+
 def _check_shapes(P, q, l_n=None, mu=None):
     if P.dim() != 3 or P.size(1) != P.size(2):
         raise ValueError(f"P must have shape (B,N,N), got {tuple(P.shape)}")
     B, N = P.size(0), P.size(1)
+    if N > MAX_N:
+        raise ValueError(f"N={N} exceeds the {MAX_N} unknowns per problem these kernels support (one problem per warp tile: "
+                         f"QPs up to N={MAX_N}, QCQPs up to {MAX_N // 2} contacts); the reference's solveQP / solveQCQP have no such limit")
     if q.dim() != 3 or tuple(q.shape) != (B, N, 1):
         raise ValueError(f"q must have shape (B,N,1)=({B},{N},1), got {tuple(q.shape)}")
     if l_n is not None:
@@ -117,12 +124,14 @@ def _check_shapes(P, q, l_n=None, mu=None):
 
 
 # --------------------------------------------------------------------------- raw batched ops
-def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None, state=None):
+def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None, state=None,
+               out=None):
     """Batched solveQP on CUDA tensors: P (B,N,N), q (B,N,1) -> x (B,N,1) [, iters (B,) int32].
-    warm_start (B,N,1), when given, is where the iteration starts (extension; None = the reference's behaviour)."""
+    warm_start (B,N,1), when given, is where the iteration starts (extension; None = the reference's behaviour).
+    out: optional contiguous (B,N,1) CUDA tensor to write x into."""
     dev = P.device
     B, N = P.size(0), P.size(1)
-    x = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
+    x = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if out is None else out
     iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
     L = _lib.load()
     with torch.cuda.device(dev):
@@ -133,11 +142,16 @@ def qp_forward(P, q, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_it
     return (x, iters) if return_iters else x
 
 
-def qp_backward(P, q, x, grad_x, need_P=True, need_q=True, state=None):
+def qp_backward(P, q, x, grad_x, need_P=True, need_q=True, state=None, out=None):
+    """Batched solveDerivativesQP + the products of qcqp.py:48-51 -> (grad_P, grad_q); out = optional (grad_P, grad_q) to fill."""
     dev = P.device
     B, N = P.size(0), P.size(1)
-    gP = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need_P else None
-    gq = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if need_q else None
+    if out is not None:
+        gP, gq = out
+        need_P, need_q = gP is not None, gq is not None
+    else:
+        gP = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need_P else None
+        gq = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if need_q else None
     if need_P or need_q:
         L = _lib.load()
         with torch.cuda.device(dev):
@@ -148,10 +162,10 @@ def qp_backward(P, q, x, grad_x, need_P=True, need_q=True, state=None):
 
 
 def qcqp_forward(P, q, l_n, mu, eps, max_iter, mu_prox=1e-7, adaptative_rho=True, return_iters=False, warm_start=None,
-                 state=None):
+                 state=None, out=None):
     dev = P.device
     B, N = P.size(0), P.size(1)
-    x = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
+    x = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if out is None else out
     iters = torch.empty((B,), dtype=torch.int32, device=dev) if return_iters else None
     L = _lib.load()
     with torch.cuda.device(dev):
@@ -162,14 +176,18 @@ def qcqp_forward(P, q, l_n, mu, eps, max_iter, mu_prox=1e-7, adaptative_rho=True
     return (x, iters) if return_iters else x
 
 
-def qcqp_backward(P, q, l_n, mu, x, grad_x, need=(True, True, True, True), state=None):
+def qcqp_backward(P, q, l_n, mu, x, grad_x, need=(True, True, True, True), state=None, out=None):
     dev = P.device
     B, N = P.size(0), P.size(1)
     nc = N // 2
-    gP = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need[0] else None
-    gq = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if need[1] else None
-    gl = torch.empty((B, nc, 1), dtype=torch.float64, device=dev) if need[2] else None
-    gm = torch.empty((B, nc, 1), dtype=torch.float64, device=dev) if need[3] else None
+    if out is not None:
+        gP, gq, gl, gm = out
+        need = tuple(t is not None for t in out)
+    else:
+        gP = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need[0] else None
+        gq = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if need[1] else None
+        gl = torch.empty((B, nc, 1), dtype=torch.float64, device=dev) if need[2] else None
+        gm = torch.empty((B, nc, 1), dtype=torch.float64, device=dev) if need[3] else None
     if any(need):
         L = _lib.load()
         with torch.cuda.device(dev):
@@ -215,28 +233,151 @@ def _back_to(t, device):
     return t.to(device)
 
 
+# --------------------------------------------------------------------------- CPU tensors: pipelined copies
+# A user of the reference holds CPU tensors.  For batches worth it the layers move P to the device in chunks on a copy
+# stream while the forward kernel already solves the chunks that have arrived, and in backward read grad_P back chunk by
+# chunk on another copy stream while later chunks are still being differentiated (the bulk of the traffic is P in and
+# grad_P out: 8 N^2 bytes per problem each; the vectors are 1/N of that and move whole).  Pinned (page-locked) input
+# tensors make the copies truly asynchronous; pageable ones work, staged by the driver.  Outputs are pinned CPU tensors.
+HOST_PIPE_MIN_BATCH = 4096  # below this a plain copy is as fast
+HOST_PIPE_CHUNKS = 6
+_side_streams = {}
+
+
+def _pipe_streams(dev):
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _side_streams[key]
+
+
+def _chunk_bounds(B, n=None):
+    n = n or HOST_PIPE_CHUNKS
+    step = -(-B // n)
+    step = max(4, (step + 3) & ~3)  # chunk starts stay 32-byte aligned for every N
+    return [(c0, min(B, c0 + step)) for c0 in range(0, B, step)]
+
+
+def _use_host_pipe(P):
+    return (not P.is_cuda) and P.size(0) >= HOST_PIPE_MIN_BATCH
+
+
+def _cpu_f64(t):
+    t = t.detach()
+    if t.dtype != torch.float64:
+        t = t.double()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _pipe_forward(dev, P, small, launch):
+    """P (CPU, (B,N,N)) to the device chunk by chunk; launch(c0, c1, Pd, smalls_dev, xd) enqueues the forward of a chunk on
+    the current stream; x comes back chunk by chunk into a pinned CPU tensor.  Returns (Pd, smalls_dev, xd, x_cpu)."""
+    B, N = P.size(0), P.size(1)
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = _pipe_streams(dev)
+    Pc = _cpu_f64(P)
+    smalls = [None if t is None else _cpu_f64(t).to(dev, non_blocking=True) for t in small]
+    Pd = torch.empty((B, N, N), dtype=torch.float64, device=dev)
+    xd = torch.empty((B, N, 1), dtype=torch.float64, device=dev)
+    x_cpu = torch.empty((B, N, 1), dtype=torch.float64, pin_memory=True)
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    for c0, c1 in _chunk_bounds(B):
+        with torch.cuda.stream(s_in):
+            Pd[c0:c1].copy_(Pc[c0:c1], non_blocking=True)
+            e_in = torch.cuda.Event()
+            e_in.record(s_in)
+        cur.wait_event(e_in)
+        launch(c0, c1, Pd, smalls, xd)
+        e_k = torch.cuda.Event()
+        e_k.record(cur)
+        s_out.wait_event(e_k)
+        with torch.cuda.stream(s_out):
+            x_cpu[c0:c1].copy_(xd[c0:c1], non_blocking=True)
+    s_out.synchronize()  # x_cpu is complete (and with it every copy and kernel issued above)
+    return Pd, smalls, xd, x_cpu
+
+
+def _pipe_backward(dev, B, N, grad_l, need_P, launch, small_shapes):
+    """launch(c0, c1, gd, gPd, smalls) enqueues the backward of a chunk; grad_P goes back chunk by chunk into a pinned CPU
+    tensor, the small gradients (shapes in small_shapes, None = not needed) whole.  Returns (grad_P_cpu, [small grads cpu])."""
+    cur = torch.cuda.current_stream(dev)
+    _, s_out = _pipe_streams(dev)
+    gd = _cpu_f64(grad_l).to(dev, non_blocking=True)
+    gPd = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need_P else None
+    gP_cpu = torch.empty((B, N, N), dtype=torch.float64, pin_memory=True) if need_P else None
+    smalls = [None if sh is None else torch.empty(sh, dtype=torch.float64, device=dev) for sh in small_shapes]
+    s_out.wait_stream(cur)
+    for c0, c1 in _chunk_bounds(B):
+        launch(c0, c1, gd, gPd, smalls)
+        if need_P:
+            e_k = torch.cuda.Event()
+            e_k.record(cur)
+            s_out.wait_event(e_k)
+            with torch.cuda.stream(s_out):
+                gP_cpu[c0:c1].copy_(gPd[c0:c1], non_blocking=True)
+    outs = []
+    for t in smalls:
+        if t is None:
+            outs.append(None)
+        else:
+            o = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+            o.copy_(t, non_blocking=True)  # on the current stream, after the last chunk's kernel
+            outs.append(o)
+    cur.synchronize()
+    s_out.synchronize()
+    return gP_cpu, outs
+
+
+def _sl(t, c0, c1):
+    return None if t is None else t[c0:c1]
+
+
 # --------------------------------------------------------------------------- autograd surface
 class QPFn2(Function):
     """min 1/2 l'Pl + q'l  s.t. l >= 0, batched.  Mirrors qcqp.py:22-52."""
 
     @staticmethod
     def forward(ctx, P, q, warm_start, eps, max_iter, mu_prox=1e-7):
-        _check_shapes(P, q)
+        B, N = _check_shapes(P, q)
         dev = _compute_device(P, q)
+        want_grad = any(ctx.needs_input_grad[:2])
+        ctx.out_device = q.device
+        ctx.host_pipe = _use_host_pipe(P) and not q.is_cuda
+        if ctx.host_pipe:
+            state = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if want_grad else None
+            ws = _layer_warm(warm_start, dev, q)
+
+            def launch(c0, c1, Pd, smalls, xd):
+                qp_forward(Pd[c0:c1], smalls[0][c0:c1], eps, max_iter, mu_prox, True, warm_start=_sl(ws, c0, c1),
+                           state=_sl(state, c0, c1), out=xd[c0:c1])
+
+            Pd, (qd,), x, x_cpu = _pipe_forward(dev, P, [q], launch)
+            ctx.save_for_backward(Pd, qd, x, state)
+            return x_cpu
         Pd, qd = _as_dev(P, dev, "P"), _as_dev(q, dev, "q")
         # forward -> backward hand-off: diag(P) of the problems solved on the diagonal path (the backward then skips P)
-        state = torch.empty_like(qd) if any(ctx.needs_input_grad[:2]) else None
+        state = torch.empty_like(qd) if want_grad else None
         x = qp_forward(Pd, qd, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q), state=state)
-        ctx.state = state
-        ctx.save_for_backward(Pd, qd, x)
-        ctx.out_device = q.device
+        ctx.save_for_backward(Pd, qd, x, state)
         return _back_to(x, q.device)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_l):
-        Pd, qd, x = ctx.saved_tensors
+        Pd, qd, x, state = ctx.saved_tensors
+        need_P, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if ctx.host_pipe and not grad_l.is_cuda and (need_P or need_q):
+            B, N = Pd.size(0), Pd.size(1)
+
+            def launch(c0, c1, gd, gPd, smalls):
+                qp_backward(Pd[c0:c1], qd[c0:c1], x[c0:c1], gd[c0:c1], state=_sl(state, c0, c1),
+                            out=(_sl(gPd, c0, c1), _sl(smalls[0], c0, c1)))
+
+            gP, (gq,) = _pipe_backward(Pd.device, B, N, grad_l, need_P, launch, [(B, N, 1) if need_q else None])
+            return gP, gq, None, None, None, None
         g = _as_dev(grad_l, Pd.device, "grad_l")
-        gP, gq = qp_backward(Pd, qd, x, g, ctx.needs_input_grad[0], ctx.needs_input_grad[1], state=ctx.state)
+        gP, gq = qp_backward(Pd, qd, x, g, need_P, need_q, state=state)
         return _back_to(gP, ctx.out_device), _back_to(gq, ctx.out_device), None, None, None, None
 
 
@@ -245,23 +386,48 @@ class QCQPFn2(Function):
 
     @staticmethod
     def forward(ctx, P, q, l_n, mu, warm_start, eps, max_iter, mu_prox=1e-7):
-        _check_shapes(P, q, l_n, mu)
+        B, N = _check_shapes(P, q, l_n, mu)
         dev = _compute_device(P, q, l_n, mu)
+        want_grad = any(ctx.needs_input_grad[:4])
+        ctx.out_device = q.device
+        ctx.host_pipe = _use_host_pipe(P) and not (q.is_cuda or l_n.is_cuda or mu.is_cuda)
+        if ctx.host_pipe:
+            state = torch.empty((B, N, 1), dtype=torch.float64, device=dev) if want_grad else None
+            ws = _layer_warm(warm_start, dev, q)
+
+            def launch(c0, c1, Pd, smalls, xd):
+                qcqp_forward(Pd[c0:c1], smalls[0][c0:c1], smalls[1][c0:c1], smalls[2][c0:c1], eps, max_iter, mu_prox, True,
+                             warm_start=_sl(ws, c0, c1), state=_sl(state, c0, c1), out=xd[c0:c1])
+
+            Pd, (qd, ld, md), x, x_cpu = _pipe_forward(dev, P, [q, l_n, mu], launch)
+            ctx.save_for_backward(Pd, qd, ld, md, x, state)
+            return x_cpu
         Pd, qd = _as_dev(P, dev, "P"), _as_dev(q, dev, "q")
         ld, md = _as_dev(l_n, dev, "l_n"), _as_dev(mu, dev, "mu")
-        state = torch.empty_like(qd) if any(ctx.needs_input_grad[:4]) else None  # forward -> backward hand-off
+        state = torch.empty_like(qd) if want_grad else None  # forward -> backward hand-off
         x = qcqp_forward(Pd, qd, ld, md, eps, max_iter, mu_prox, True, warm_start=_layer_warm(warm_start, dev, q),
                          state=state)
-        ctx.state = state
-        ctx.save_for_backward(Pd, qd, ld, md, x)
-        ctx.out_device = q.device
+        ctx.save_for_backward(Pd, qd, ld, md, x, state)
         return _back_to(x, q.device)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_l):
-        Pd, qd, ld, md, x = ctx.saved_tensors
+        Pd, qd, ld, md, x, state = ctx.saved_tensors
+        need = tuple(ctx.needs_input_grad[:4])
+        if ctx.host_pipe and not grad_l.is_cuda and any(need):
+            B, N = Pd.size(0), Pd.size(1)
+            nc = N // 2
+
+            def launch(c0, c1, gd, gPd, smalls):
+                qcqp_backward(Pd[c0:c1], qd[c0:c1], ld[c0:c1], md[c0:c1], x[c0:c1], gd[c0:c1], state=_sl(state, c0, c1),
+                              out=(_sl(gPd, c0, c1), _sl(smalls[0], c0, c1), _sl(smalls[1], c0, c1), _sl(smalls[2], c0, c1)))
+
+            shapes = [(B, N, 1) if need[1] else None, (B, nc, 1) if need[2] else None, (B, nc, 1) if need[3] else None]
+            gP, (gq, gl, gm) = _pipe_backward(Pd.device, B, N, grad_l, need[0], launch, shapes)
+            return gP, gq, gl, gm, None, None, None, None
         g = _as_dev(grad_l, Pd.device, "grad_l")
-        gP, gq, gl, gm = qcqp_backward(Pd, qd, ld, md, x, g, tuple(ctx.needs_input_grad[:4]), state=ctx.state)
+        gP, gq, gl, gm = qcqp_backward(Pd, qd, ld, md, x, g, need, state=state)
         o = ctx.out_device
         return _back_to(gP, o), _back_to(gq, o), _back_to(gl, o), _back_to(gm, o), None, None, None, None
 
@@ -291,6 +457,7 @@ class BoxQPFn2(Function):
         return _back_to(x, q.device)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_l):
         Pd, qd, lo, hi, x = ctx.saved_tensors
         g = _as_dev(grad_l, Pd.device, "grad_l")

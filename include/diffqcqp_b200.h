@@ -130,6 +130,15 @@ int dq_boxqp_backward(const double* P, const double* q, const double* l_min, con
                       double* grad_l_min, double* grad_l_max, int64_t B, int32_t N, void* stream);
 
 /*
+ * dq_boxqp_backward plus the two vectors the reference's per-problem binding returns (pybindings.cpp:39-45):
+ * gamma (B,2N) = dualFromPrimalBoxQP's duals [lower bounds ; upper bounds] and dgamma (B,2N) = blgamma[:2N] of
+ * solveDerivativesBoxQP (zero where a bound is inactive).  Either may be NULL.
+ */
+int dq_boxqp_backward_ex(const double* P, const double* q, const double* l_min, const double* l_max, const double* x,
+                         const double* grad_x, double* grad_P, double* grad_q, double* grad_l_min, double* grad_l_max,
+                         double* gamma, double* dgamma, int64_t B, int32_t N, void* stream);
+
+/*
  * dq_qcqp_backward plus the two intermediate vectors the reference's per-problem binding returns
  * (pybindings.cpp:62-71): gamma (B,N/2) = dualFromPrimalQCQP and dgamma (B,N/2) = blgamma[:nc] of
  * solveDerivativesQCQP; blgamma[nc:] is -grad_q and E1 = diag(2 gamma l_n^2 mu), E2 = diag(2 gamma l_n mu^2)
@@ -179,7 +188,7 @@ int64_t dq_launch_count(void);
 
 /*
  * Forward kernel selection (process-wide; for tests and A/B timing).  0 = automatic: at N == 8 with a 32-byte aligned P
- * and no warm start, batches of >= 32768 QP / Box QP problems run the thread-per-problem kernel (one problem per thread,
+ * and no warm start, batches of >= 65536 QP / Box QP problems run the thread-per-problem kernel (one problem per thread,
  * stragglers finished on 8-lane tiles), smaller ones the persistent-CTA tile kernel (diagonal batches on refilled tile
  * slots); everything else the generic kernel.  1 = generic kernel only.  2 = persistent tile kernel wherever it applies
  * (also the QCQP at N == 8).  3 = thread-per-problem kernel wherever it applies (also the QCQP at N == 8, any batch size).
@@ -191,7 +200,8 @@ int dq_set_forward_path(int path);
  * Tuning knobs of the forward kernels (process-wide; for tests and A/B timing; results do not depend on them).
  *   key 0: iterations after which the thread-per-problem kernel parks a still-running problem for its tile phase
  *          (default 48; 0 = never)
- *   key 1: smallest batch the automatic path gives to the thread-per-problem kernel (default 32768)
+ *   key 1: smallest batch the automatic path gives to the thread-per-problem kernel (default 65536)
+ *   key 2: elements of a problem each lane of that kernel holds: 8 (one thread per problem) or 4 (a lane pair)
  * Returns the previous value, -1 for an unknown key.
  */
 int64_t dq_set_forward_tuning(int32_t key, int64_t value);

@@ -12,6 +12,7 @@ ap.add_argument("--caps", default="0,24,32,48,64,96")
 ap.add_argument("--batches", default="65536")
 ap.add_argument("--gen", default="qp_diag")
 ap.add_argument("--paths", default="2,3")
+ap.add_argument("--elems", default="8")
 a = ap.parse_args()
 L = _lib.load()
 dev = torch.device("cuda", 0)
@@ -39,11 +40,12 @@ for B in [int(b) for b in a.batches.split(",")]:
     configs = []
     for path in [int(p) for p in a.paths.split(",")]:
         if path == 3:
-            configs += [(3, int(c)) for c in a.caps.split(",")]
+            configs += [(3, int(c), int(e)) for e in a.elems.split(",") for c in a.caps.split(",")]
         else:
-            configs.append((path, None))
-    for path, cap in configs:
+            configs.append((path, None, 8))
+    for path, cap, elems in configs:
         L.dq_set_forward_path(path)
+        L.dq_set_forward_tuning(2, elems)
         if cap is not None:
             L.dq_set_forward_tuning(0, cap)
         fwd(sets[0], it.data_ptr()); torch.cuda.synchronize()
@@ -72,7 +74,8 @@ for B in [int(b) for b in a.batches.split(",")]:
             ev = torch.cuda.Event(); ev.record(st); torch.cuda.current_stream(dev).wait_event(ev)
         e1.record()
         torch.cuda.synchronize()
-        print(f"  path {path} cap {cap}: bit-identical to generic {same}; isolated us median {ts[len(ts)//2]:.1f} min {ts[0]:.1f}; "
+        print(f"  path {path} E {elems} cap {cap}: bit-identical to generic {same}; isolated us median {ts[len(ts)//2]:.1f} min {ts[0]:.1f}; "
               f"4-stream us/launch {e0.elapsed_time(e1) * 1e3 / 400:.1f}", flush=True)
     L.dq_set_forward_path(0)
     L.dq_set_forward_tuning(0, 48)
+    L.dq_set_forward_tuning(2, 8)

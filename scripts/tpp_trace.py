@@ -11,6 +11,7 @@ cap = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 ADAPT = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 MAXIT = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
+ELEMS = int(sys.argv[5]) if len(sys.argv) > 5 else 8
 L = _lib.load()
 dev = torch.device("cuda", 0)
 B, N = 65536, 8
@@ -19,7 +20,8 @@ x = torch.empty(B, N, 1, dtype=torch.float64, device=dev)
 sp = torch.cuda.current_stream(dev).cuda_stream
 L.dq_set_forward_path(3)
 L.dq_set_forward_tuning(0, cap)
-buf = torch.zeros(4096 * 8 * 16, dtype=torch.int64, device=dev)
+L.dq_set_forward_tuning(2, ELEMS)
+buf = torch.zeros(8192 * 8 * 32, dtype=torch.int64, device=dev)
 L.dq_debug_set_trace.argtypes = [ctypes.c_void_p]
 for k in range(3):
     assert L.dq_qp_forward(P.data_ptr(), q.data_ptr(), None, x.data_ptr(), None, B, N, 1e-7, 1e-7, MAXIT, ADAPT, sp) == 0
@@ -31,7 +33,7 @@ assert L.dq_qp_forward(P.data_ptr(), q.data_ptr(), None, x.data_ptr(), None, B, 
 e1.record()
 torch.cuda.synchronize()
 print(f"cap_it {cap}: launch {e0.elapsed_time(e1) * 1e3:.1f} us (event to event)")
-t = buf.cpu().numpy().reshape(-1, 16)
+t = buf.cpu().numpy().reshape(-1, 32)
 t = t[t[:, 0] > 0]
 nw = t.shape[0]
 t0 = t[:, 0].min()
@@ -51,3 +53,11 @@ print(f"  trips per warp: mean {trips.mean():.1f} p50 {np.median(trips):.0f} max
       f"us/trip (p50 loop / p50 trips) {np.median(d[:, 4]) / max(1, np.median(trips)):.3f}")
 ns = t[::W, 9]
 print(f"  parked per CTA: mean {ns.mean():.1f} max {ns.max()}")
+acc = t[:, 10:15].astype(np.float64)
+nm = ["body", "decisions", "update", "fin/park", "refill"]
+tot = acc.sum(1)
+print("  cycles per trip (lane-0 clock64, mean over warps): " + ", ".join(f"{n} {(acc[:, k] / np.maximum(trips, 1)).mean():.0f}" for k, n in enumerate(nm))
+      + f"; sum {(tot / np.maximum(trips, 1)).mean():.0f}")
+uu = t[:, 16:19].astype(np.float64)
+print("  update section split (cycles per trip): " + ", ".join(f"{n} {(uu[:, k] / np.maximum(trips, 1)).mean():.0f}"
+      for k, n in enumerate(["scalar part + post + sync", "shared items", "sync + pickup"])))

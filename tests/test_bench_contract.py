@@ -51,3 +51,22 @@ def test_gpu_arm_refuses_to_run_without_a_device():
         return
     r = _run("--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_both_arms_print_the_same_config():
+    """`config` is built by one function for both arms (the driver compares them); the rotating-set rule keeps every set
+    on one stream (R a multiple of S) with a footprint above the 126 MB L2."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    for wl_name, streams in (("qp_diag_n8", 4), ("qcqp_n24", 4), ("qcqp_n32", 3)):
+        a = argparse.Namespace(workload=wl_name, batch=0, streams=streams)
+        kind, B, N, _, _ = bench.WORKLOADS[wl_name]
+        R, S, nbytes = bench.rotating_sets(kind, B, N, streams)
+        assert R % S == 0 and R >= S >= 1 and (R * nbytes > 126e6 or R == 16)
+        c = bench.common_config(a, 1)
+        assert set(c) == {"workload", "name", "B_per_gpu", "N", "eps", "max_iter", "sharding", "l2_policy"}
+    r = _run("--impl", "reference", "--batch", "1024", "--steps", "1", "--warmup", "1")
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    a = argparse.Namespace(workload="qp_diag_n8", batch=1024, streams=4)
+    assert d["config"] == bench.common_config(a, 1)
