@@ -103,8 +103,11 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
 
   double dl;  // this lane's entry of bl
   if (!dense) {
-    // gamma = -(P l + q), zeroed where l_i > eps  (Solver.cpp:125-134)
-    double gamma = -(pdiag * xi + qi);
+    // gamma = -(P l + q), zeroed where l_i > eps  (Solver.cpp:125-134).  FMA policy, as in the forward: a value that the
+    // reference compares against a threshold to take a branch (here the active set, gamma < -1e-10) is formed with the
+    // reference's own roundings -- product and sum rounded separately, as an x86-64 build without FMA does; the linear
+    // algebra behind it (normal equations, refinement) may contract.
+    double gamma = -__dadd_rn(__dmul_rn(pdiag, xi), qi);
     if (xi > EPS_ACT) gamma = 0.0;
     const bool act = valid && (gamma < -1e-10);  // not_null, Solver.cpp:140
     const bool fr = valid && !act;               // null_idx

