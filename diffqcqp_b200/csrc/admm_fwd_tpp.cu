@@ -31,8 +31,21 @@ namespace dq {
 #ifndef DQ_TPP_PPS4
 #define DQ_TPP_PPS4 7  // capacity: quarter-problems per problem slot a CTA's chunk may hold (7 -> 1.75 problems per slot)
 #endif
-constexpr int TPP_WARPS = DQ_TPP_WARPS;
-constexpr int TPP_THREADS = 32 * TPP_WARPS;
+// Extra warps per CTA that run the head of the queue (the predicted-slowest problems, among them the batch's 500-iteration
+// stragglers) on 8-lane tiles from the start, so that they overlap the bulk instead of trailing it.  Measured at B = 65536
+// (profiles/r02_tpp_experiments.txt): with one such warp an isolated launch takes 114 instead of 131 us (the tile phase after
+// the main loop shrinks from <= 45 to <= 17 us), but the main loop slows from 55 to 64 us (a fifth warp per CTA at three
+// CTAs per SM caps the kernel at 128 registers and shares the issue slots), so back-to-back launches cost 72 instead of
+// 62 us.  Off by default: throughput is the headline; a caller whose batches are strictly sequential can build with 1.
+#ifndef DQ_TPP_TILE_WARPS
+#define DQ_TPP_TILE_WARPS 0
+#endif
+constexpr int TPP_WARPS = DQ_TPP_WARPS;             // warps that run the main (slot) loop
+constexpr int TPP_TWARPS = DQ_TPP_TILE_WARPS;       // tile warps
+constexpr int TPP_NWARPS = TPP_WARPS + TPP_TWARPS;
+constexpr int TPP_THREADS = 32 * TPP_WARPS;         // threads of the main loop
+constexpr int TPP_BLOCK = 32 * TPP_NWARPS;
+constexpr int TPP_HEAD = 4 * TPP_TWARPS;            // queue positions (= dump slots) the tile warps start on
 constexpr int TPP_STRAG = 8 * TPP_WARPS;  // parked stragglers per CTA (two rounds of the tile phase)
 constexpr int TPP_SD = 25;                // doubles per parked problem (l_2, u, q_prox), odd stride
 
@@ -49,7 +62,7 @@ struct TppGeo {
 #ifdef DQ_TPP_CTAS
   static constexpr int CTAS = DQ_TPP_CTAS;
 #else
-  static constexpr int CTAS = E == 8 ? 3 : (E == 4 ? 5 : 8);  // resident CTAs per SM the register budget is sized for
+  static constexpr int CTAS = E == 8 ? 3 : 4;  // resident CTAs per SM the register budget is sized for
 #endif
 };
 
@@ -71,7 +84,7 @@ struct TppRec {  // one problem's record in shared memory, in doubles
   static constexpr int D = USED | 1;  // odd stride: thread j reading rec[j * D + i] hits 32 distinct bank pairs
   static constexpr size_t bytes = (size_t)(CAP * D + TPP_STRAG * TPP_SD) * sizeof(double) +
                                   (size_t)(2 * CAP + 4 * TPP_STRAG + TPP_THREADS + 8 + 32) * sizeof(int);
-  static_assert(CAP * D >= TPP_WARPS * FwdSmem<8>::per_warp_doubles, "the records double as the generic path's scratch");
+  static_assert(CAP * D >= TPP_NWARPS * FwdSmem<8>::per_warp_doubles, "the records double as the generic path's scratch");
 };
 
 // sum of eight values in the order of tile_sum<8>'s xor butterfly (offsets 4, 2, 1): bit-identical to the tile kernels
@@ -178,7 +191,7 @@ __device__ __forceinline__ unsigned long long tpp_now() {
 }
 #define TPP_MARK(k, v)                                                                      \
   do {                                                                                      \
-    if (g_tpp_trace != nullptr && lane == 0) g_tpp_trace[((size_t)blockIdx.x * TPP_WARPS + warp) * 32 + (k)] = (v); \
+    if (g_tpp_trace != nullptr && lane == 0) g_tpp_trace[((size_t)blockIdx.x * TPP_NWARPS + warp) * 32 + (k)] = (v); \
   } while (0)
 #else
 #define TPP_MARK(k, v) \
@@ -199,7 +212,7 @@ __device__ __forceinline__ unsigned long long tpp_now() {
 #endif
 
 template <int PROX, int E>
-__global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_kernel(const FwdParams p, const int cap_it) {
+__global__ void __launch_bounds__(TPP_BLOCK, TppGeo<E>::CTAS) admm_fwd_tpp8_kernel(const FwdParams p, const int cap_it) {
   using R = TppRec<PROX, E>;
   using G = TppGeo<E>;
   constexpr bool QCQP = (PROX == PROX_DISK);
@@ -226,9 +239,10 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
 
   TPP_MARK(0, tpp_now());
   if (tid == 0) {
-    ctl[0] = nb < G::SLOTS ? nb : G::SLOTS;  // the first queue positions go to the slots directly
+    const int first = TPP_HEAD + G::SLOTS;  // the first queue positions go to the tile warps' tiles and to the slots directly
+    ctl[0] = nb < first ? nb : first;
     ctl[1] = 0;
-    ctl[2] = 0;
+    ctl[2] = TPP_HEAD;  // dump slots 0 .. TPP_HEAD - 1 belong to the tile warps' first problems
   }
   if (tid < 32) hist[tid] = 0;
   __syncthreads();
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
     const int r = (lane & 15) >> 1;
     const bool has_diag = (r >> 2) == (lane & 1);
     const int d = r & 3;
-    for (int w0 = warp * 16; w0 < nb; w0 += TPP_WARPS * 16) {
+    for (int w0 = warp * 16; w0 < nb; w0 += TPP_NWARPS * 16) {
       const int nw = nb - w0 < 16 ? nb - w0 : 16;
       const double* src = p.P + (b0 + w0) * 64 + lane * 4;
       double v[8][4];
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
   // ---- 2. per-problem constants, one problem per thread: q (and the prox data), lambda_max by power iteration
   // (Solver.cpp:46-59, rescaled by exact powers of two as in solve_group), rho_0 / tau_0 (:72-73, :531-532),
   // P += (rho + mu) I and its inverse (:75-77), the queue-order key
-  for (int j = tid; j < nb; j += TPP_THREADS) {
+  for (int j = tid; j < nb; j += TPP_BLOCK) {
     double* rec = recs + j * R::D;
     const long long e0 = (b0 + j) * 8;
     double pd[8], qv[8], w[8];
@@ -397,7 +411,7 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
     hist[31 - lane] = incl - cnt;
   }
   __syncthreads();
-  for (int t = tid; t < nb; t += TPP_THREADS) {
+  for (int t = tid; t < nb; t += TPP_BLOCK) {
     const unsigned k = keys[t];
     order[hist[k >> 16] + (int)(k & 0xffffu)] = t;
   }
@@ -406,8 +420,9 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
 
   // ---- 3. the ADMM loop (Solver.cpp:79-121 / :538-580): a slot of LT = 8 / E adjacent lanes per problem, lane h of a slot
   // holding elements E h .. E h + E - 1.  Everything per-problem (residual maxima, decisions, rho, counters) is computed by
-  // every lane of the slot with identical bits, so control flow is slot-uniform.
-  {
+  // every lane of the slot with identical bits, so control flow is slot-uniform.  (The tile warps -- warps 0 .. TPP_TWARPS - 1 -- go to 4. directly.)
+  if (warp >= TPP_TWARPS) {
+    const int mtid = tid - 32 * TPP_TWARPS;  // thread index among the main-loop warps
     const int h = lane & (LT - 1);
     const int eo = E * h;                    // this lane's first element
     const int slot_lane = lane & ~(LT - 1);  // first lane of this lane's slot
@@ -444,8 +459,8 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
 #define DQ_TPP_REFILL 2  // power of two
 #endif
     bool done = true;  // nothing more to take from the queue
-    if (tid / LT < nb) {
-      take(tid / LT);
+    if (TPP_HEAD + mtid / LT < nb) {  // (queue positions 0 .. TPP_HEAD - 1, the predicted-slowest problems, run on the tile warps)
+      take(TPP_HEAD + mtid / LT);
       done = false;
     }
     unsigned ntrips = 0;
@@ -453,7 +468,7 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
     unsigned long long acc_body = 0, acc_dec = 0, acc_upd = 0, acc_fin = 0, acc_refill = 0, acc_u1 = 0, acc_u2 = 0, acc_u3 = 0;
 #endif
 
-    int* ul = ulist + warp * 32;  // problems posted for a rho update in the current trip
+    int* ul = ulist + (warp - TPP_TWARPS) * 32;  // problems posted for a rho update in the current trip
     // one posted item: e < 8 diagonal entry (m += c, then (1/s)(1/s), s = sqrt(m): LLT of a diagonal matrix and the two
     // substitutions against I), e == 8: 1 / rho, e == 9: 1 / (tau_dec after its next decay)
     auto item_load = [&](int item, int nit, double*& r, int& e, bool& v) -> double {
@@ -678,14 +693,12 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
     TPP_MARK(5, tpp_now());
     TPP_MARK(8, (unsigned long long)ntrips);
   }
-  __syncthreads();
-  TPP_MARK(6, tpp_now());
-
-  // ---- 4. parked problems, on 8-lane tiles (lane = element), four per warp, one round per 4 * TPP_WARPS of them.
-  // Same loop as admm_fwd_diag8_kernel's: the next iterate is computed before the pending one is decided, the tile maximum
-  // is a 64-bit butterfly, or two full-mask redux when the warp is down to one live tile.
+  // ---- 4. 8-lane tiles (lane = element), four per warp, for the problems that run long: the head of the queue (the
+  // problems predicted slowest: the batch's 500-iteration stragglers are among them) on the tile warps from the start, so
+  // that they overlap the bulk instead of trailing it, and the problems the main loop parked, on all warps, once the
+  // CTA's queue has drained.  Same iteration as admm_fwd_diag8_kernel's: the next iterate is computed before the pending
+  // one is decided, the tile maximum is a 64-bit butterfly, or two full-mask redux when the warp is down to one live tile.
   {
-    const int ns = ctl[2] < TPP_STRAG ? ctl[2] : TPP_STRAG;
     const int ti = lane & 7, tp = lane >> 3, tile_base = tp * 8;
     const bool odd = lane & 1;
     unsigned tmask = 0xffu << tile_base;
@@ -693,18 +706,14 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
     struct Iter {
       double l2, u, qprox, dl, du, l;
     };
-    for (int r0 = 0; r0 < ns; r0 += 4 * TPP_WARPS) {  // CTA-uniform
-      const int s = r0 + tp * TPP_WARPS + warp;        // stragglers are dealt one per warp first: lone tiles run the latency loop
-      int nlive = 0;
-#pragma unroll
-      for (int t = 0; t < 4; t++) nlive += (r0 + t * TPP_WARPS + warp) < ns;
-      if (nlive == 0) continue;  // warp-uniform
+    // one round: this lane's tile runs dump slot s (if has) to the end; nlive = tiles of the warp that have one (warp-uniform)
+    auto tile_round = [&](const int s, const bool has, int nlive) {
       double qi = 0.0, pinvd = 1.0, rho = 1.0, irho = 1.0, x0 = 0.0, x1 = 0.0, x2 = 0.0;
       int live = 0, rho_up = 0, cpt5 = 0, it = 0, ridx = 0;
       double* rec = recs;
       Iter A, B;
       A.l2 = A.u = A.qprox = A.dl = A.du = A.l = 0.0;
-      if (s < ns) {
+      if (has) {
         ridx = sinfo[4 * s];
         it = sinfo[4 * s + 1];
         cpt5 = sinfo[4 * s + 2];
@@ -844,6 +853,38 @@ __global__ void __launch_bounds__(TPP_THREADS, TppGeo<E>::CTAS) admm_fwd_tpp8_ke
         body(A, B, std::false_type{});
       }
       __syncwarp();
+    };
+
+    if (warp < TPP_TWARPS) {  // a tile warp: queue positions (= dump slots) 4 warp + tp, from their initial state.  (Tile warps
+      // are the CTA's lowest-numbered warps: the SM's warp arbiter favours high warp ids, so the main loop keeps priority.)
+      const int s = 4 * warp + tp;
+      const bool has = s < nb;
+      if (has) {
+        const int ridx = order[s];
+        double* sd = sdump + s * TPP_SD;
+        sd[ti] = 0.0;                              // l_2 = u = 0, q_prox = q   :67-74
+        sd[8 + ti] = 0.0;
+        sd[16 + ti] = recs[ridx * R::D + R::Q + ti];
+        if (ti == 0) {
+          sinfo[4 * s] = ridx;
+          sinfo[4 * s + 1] = 0;
+          sinfo[4 * s + 2] = 0;
+          sinfo[4 * s + 3] = 0;
+        }
+      }
+      __syncwarp();
+      const int nl = nb - 4 * warp;
+      if (nl > 0) tile_round(s, has, nl < 4 ? nl : 4);
+    }
+    __syncthreads();  // the main loops have drained the queue: what they parked is complete
+    TPP_MARK(6, tpp_now());
+    const int ns = ctl[2] < TPP_STRAG ? ctl[2] : TPP_STRAG;
+    for (int r0 = TPP_HEAD; r0 < ns; r0 += 4 * TPP_NWARPS) {  // CTA-uniform; stragglers are dealt one per warp first: lone tiles run the latency loop
+      const int s = r0 + tp * TPP_NWARPS + warp;
+      int nlive = 0;
+#pragma unroll
+      for (int t = 0; t < 4; t++) nlive += (r0 + t * TPP_NWARPS + warp) < ns;
+      if (nlive > 0) tile_round(s, s < ns, nlive);
     }
     TPP_MARK(9, (unsigned long long)ns);
   }
@@ -915,7 +956,7 @@ static cudaError_t launch_tpp8_t(const FwdParams& p, cudaStream_t stream) {
   long long grid = sms * k;
   if (grid > p.B) grid = p.B;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  admm_fwd_tpp8_kernel<PROX, E><<<(unsigned)grid, TPP_THREADS, TppRec<PROX, E>::bytes, stream>>>(p, g_tpp_cap_it);
+  admm_fwd_tpp8_kernel<PROX, E><<<(unsigned)grid, TPP_BLOCK, TppRec<PROX, E>::bytes, stream>>>(p, g_tpp_cap_it);
   return cudaGetLastError();
 }
 

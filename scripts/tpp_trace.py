@@ -39,6 +39,7 @@ nw = t.shape[0]
 t0 = t[:, 0].min()
 rel = (t[:, :8] - t0) / 1e3  # us
 names = ["start", "P read done", "after sync", "setup done", "sorted", "thread loop done", "after sync", "end"]
+W = W + int(os.environ.get("TPP_TILE_WARPS", "0"))  # + the tile warps of each CTA
 print(f"{nw} warps ({nw // W} CTAs)")
 for k, nm in enumerate(names):
     c = rel[:, k]
