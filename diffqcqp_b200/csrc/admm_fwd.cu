@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIA
     __syncthreads();
     if (ctl[1] != 0 || p.max_iter <= 0) {  // a dense problem in the batch (or nothing to iterate): the generic path,
       __syncthreads();                     // groups of four handed to the warps as they become free
+      if (threadIdx.x == 0 && ctl[1] != 0 && p.dense_hint != nullptr) *(volatile int*)p.dense_hint = 1;  // tell the host (launch_admm_fwd)
       if (threadIdx.x == 0) ctl[0] = 0;
       __syncthreads();
       while (true) {
@@ -510,11 +511,59 @@ static cudaError_t launch_diag8(const FwdParams& p, cudaStream_t stream) {
 }
 
 // prox: 0 = x >= 0 (QP), 1 = per-contact disks (QCQP), 2 = box, 3 = box + sign constraint
-cudaError_t launch_admm_fwd(const FwdParams& p, int prox, int T, cudaStream_t stream) {
+// The N == 8 fast paths (thread-per-problem, persistent tiles) are built for diagonal P; a dense batch costs them their flat
+// read of P plus a hand-out of groups inside low-occupancy CTAs (8-15 % slower than the generic kernel, whose 32 warps per
+// SM suit the dense arithmetic).  Whether P is dense is only known on the device, so the kernels report it: they set a
+// flag in page-locked host memory (mapped into the device) when they fall back to the group routine, and the launcher,
+// which reads the flag without synchronising -- it sees the outcome of launches that have completed by now -- sends the
+// next DENSE_HOLD N == 8 launches to the generic kernel, then probes the fast path again.  Results do not depend on the
+// path (bit-identical), so a stale or racy read only costs time.  dq_set_forward_path overrides.
+struct DenseHint {
+  int* flag = nullptr;  // page-locked, device-visible at the same address (unified addressing)
+  int hold = 0;         // launches still to be sent to the generic kernel
+};
+static DenseHint g_dense_hint[64];
+constexpr int DENSE_HOLD = 64;
+
+static bool n8_batches_look_dense(int dev, cudaStream_t stream, int** flag_out) {
+  DenseHint& h = g_dense_hint[dev];
+  *flag_out = nullptr;
+  if (h.flag == nullptr) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {  // no allocation inside a graph capture
+      (void)cudaGetLastError();
+      return false;
+    }
+    if (cudaHostAlloc((void**)&h.flag, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      (void)cudaGetLastError();
+      h.flag = nullptr;
+      *flag_out = nullptr;
+      return false;
+    }
+    *h.flag = 0;
+  }
+  *flag_out = h.flag;
+  if (*(volatile int*)h.flag != 0) {
+    *(volatile int*)h.flag = 0;
+    h.hold = DENSE_HOLD;
+  }
+  if (h.hold > 0) {
+    --h.hold;
+    return true;
+  }
+  return false;
+}
+
+cudaError_t launch_admm_fwd(const FwdParams& p_in, int prox, int T, cudaStream_t stream) {
+  FwdParams p = p_in;
   // N == 8, QP / Box prox: persistent CTAs, diagonal batches on refilled tile slots, dense batches via solve_group.
   // The disk prox (QCQP) stays on the generic kernel: its iteration counts are too even for the refill to pay
   // (measured: 116 us vs 98 us per 65536 diagonal problems).  g_fwd_path == 2 forces the persistent kernel for it too.
-  const bool n8 = p.N == 8 && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0 && p.warm == nullptr;
+  bool n8 = p.N == 8 && (reinterpret_cast<uintptr_t>(p.P) & 31u) == 0 && p.warm == nullptr;
+  if (n8 && g_fwd_path == 0) {  // automatic path only: forced paths (tests, A/B timing) stay what they were asked to be
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && n8_batches_look_dense(dev, stream, &p.dense_hint)) n8 = false;
+  }
   // N == 8, large batches: one problem per thread (admm_fwd_tpp.cu) -- 2.4x fewer instructions per solve than the tile
   // kernels, but a lane owns a whole problem, so it needs >= ~1 problem per thread slot of the device to pay
   if (n8 && (g_fwd_path == 3 || (g_fwd_path == 0 && p.B >= g_tpp_min_batch && prox != PROX_DISK)))

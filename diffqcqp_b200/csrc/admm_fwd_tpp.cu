@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(TPP_BLOCK, TppGeo<E>::CTAS) admm_fwd_tpp8_kern
   TPP_MARK(2, tpp_now());
   if (ctl[1] != 0 || p.max_iter <= 0) {  // a dense problem in the chunk (or nothing to iterate): the generic group routine,
     __syncthreads();                     // groups of four handed to the warps as they become free
+    if (tid == 0 && ctl[1] != 0 && p.dense_hint != nullptr) *(volatile int*)p.dense_hint = 1;  // tell the host (launch_admm_fwd)
     if (tid == 0) ctl[0] = 0;
     __syncthreads();
     while (true) {

@@ -59,6 +59,7 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
   p.lo = l_min; p.hi = l_max; p.vsign = v;
   p.warm = warm ? warm_start : nullptr;
   p.state = state;
+  p.dense_hint = nullptr;  // filled in by launch_admm_fwd
   p.B = B; p.N = N; p.eps = eps; p.mu_prox = mu_prox; p.max_iter = max_iter;
   p.adaptive = (adaptive & DQ_FLAG_ADAPTIVE_RHO) ? 1 : 0;
   p.n_groups = (B + G - 1) / G;
