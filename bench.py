@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="(N=1, default workload) skip the short runs of BASELINE configs[2] and [3]")
     ap.add_argument("--no-cfg5", action="store_true", help="(N>1) skip the BASELINE configs[4] section (B=262144/GPU N=16 QCQP, "
                                                           "shard-resident and scatter-inclusive)")
     ap.add_argument("--scatter", action="store_true",
@@ -354,6 +355,85 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- BASELINE configs[2] and [3] at N = 1
+def time_workload(L, dev, kind, gen, B, N, steps, warmup, nsets=2, seed0=9000):
+    """fwd + bwd of one batch shape on one stream: ms per step (CUDA events), `nsets` rotating input sets."""
+    import torch
+    from diffqcqp_b200 import _lib
+
+    nc = N // 2
+    sets, host0 = [], None
+    for r in range(nsets):
+        inp = make_inputs(kind, gen, B, N, seed=seed0 + r)
+        host0 = host0 or inp
+        d = {k: v.to(dev) for k, v in inp.items()}
+        d.update(x=torch.empty((B, N, 1), dtype=torch.float64, device=dev), st=torch.empty((B, N, 1), dtype=torch.float64, device=dev),
+                 gP=torch.empty((B, N, N), dtype=torch.float64, device=dev), gq=torch.empty((B, N, 1), dtype=torch.float64, device=dev))
+        if kind == "qcqp":
+            d.update(gl=torch.empty((B, nc, 1), dtype=torch.float64, device=dev), gm=torch.empty((B, nc, 1), dtype=torch.float64, device=dev))
+        sets.append(d)
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    def step(d):
+        if kind == "qp":
+            _lib.check(L.dq_qp_forward_ex(d["P"].data_ptr(), d["q"].data_ptr(), None, d["x"].data_ptr(), None, d["st"].data_ptr(),
+                                          B, N, EPS, MU_PROX, MAX_ITER, 1, sp), "forward")
+            _lib.check(L.dq_qp_backward_ex(d["P"].data_ptr(), d["q"].data_ptr(), d["x"].data_ptr(), d["g"].data_ptr(), d["st"].data_ptr(),
+                                           d["gP"].data_ptr(), d["gq"].data_ptr(), B, N, sp), "backward")
+        else:
+            _lib.check(L.dq_qcqp_forward_ex(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(), None,
+                                            d["x"].data_ptr(), None, d["st"].data_ptr(), B, N, EPS, MU_PROX, MAX_ITER, 1, sp), "forward")
+            _lib.check(L.dq_qcqp_backward_ex2(d["P"].data_ptr(), d["q"].data_ptr(), d["l_n"].data_ptr(), d["mu"].data_ptr(),
+                                              d["x"].data_ptr(), d["g"].data_ptr(), d["st"].data_ptr(), d["gP"].data_ptr(),
+                                              d["gq"].data_ptr(), d["gl"].data_ptr(), d["gm"].data_ptr(), None, None, B, N, sp), "backward")
+
+    for k in range(warmup):
+        step(sets[k % nsets])
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(steps):
+        step(sets[k % nsets])
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    del sets
+    torch.cuda.empty_cache()
+    return ms, host0
+
+
+def run_other_configs(L, dev, cpu_budget_s=2.0):
+    """BASELINE configs[2] (B=65536 N=24 QCQP) and configs[3] (B=262144 N=32 mixed: 131072 QPs + 131072 QCQPs) on one B200:
+    a few steps each, device-resident, with a bounded sample of the reference's CPU path beside each."""
+    peak, _ = hbm_peak()
+    out = {}
+    parts = {}
+    for name in ("qcqp_n24", "qp_dense_n32", "qcqp_n32"):
+        kind, B, N, kw, desc = WORKLOADS[name]
+        ms, host0 = time_workload(L, dev, kind, kw["gen"], B, N, steps=6, warmup=3)
+        fb, bb = alg_bytes(kind, N)
+        ent = {"workload": desc, "B": B, "N": N, "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "solves/s",
+               "step_frac_hbm": (fb + bb) * B / (ms * 1e-3) / 1e9 / peak, "timing": "6 steps after 3 warm-ups, one stream, 2 rotating input sets"}
+        eng, ckind, a, n, reps = cpu_sample(kind, host0, B, cpu_budget_s)
+        dt = sum(cpu_pass(eng, kind, a) for _ in range(reps))
+        ent["cpu_baseline"] = {"value": n * reps / dt, "unit": "solves/s", "cores": host_threads(), "kind": ckind,
+                               "sample": f"{reps} x (fwd+bwd over the first {n} of {B} problems), {dt:.1f} s"}
+        parts[name] = ent
+        del host0
+    out["configs[2] B=65536 N=24 QCQP"] = parts["qcqp_n24"]
+    t4 = parts["qp_dense_n32"]["ms_per_step"] + parts["qcqp_n32"]["ms_per_step"]
+    b4 = parts["qp_dense_n32"]["B"] + parts["qcqp_n32"]["B"]
+    cpu4 = b4 / (parts["qp_dense_n32"]["B"] / parts["qp_dense_n32"]["cpu_baseline"]["value"]
+                 + parts["qcqp_n32"]["B"] / parts["qcqp_n32"]["cpu_baseline"]["value"])
+    out["configs[3] B=262144 N=32 mixed QP/QCQP"] = {
+        "ms_per_step": t4, "value": b4 / (t4 * 1e-3), "unit": "solves/s", "B": b4,
+        "cpu_baseline": {"value": cpu4, "unit": "solves/s", "cores": host_threads(), "kind": parts["qcqp_n32"]["cpu_baseline"]["kind"]},
+        "note": "warm_start is dead in the reference (Solver.cpp:70 -> :80): the warm-started solve is the same computation",
+        "qp_half": parts["qp_dense_n32"], "qcqp_half": parts["qcqp_n32"]}
+    return out
 
 
 # ------------------------------------------------------------------------------- BASELINE configs[4] at N > 1
@@ -788,6 +868,8 @@ def run_b200_arm(args):
         }
         if cfg5 is not None:
             line["cfg5"] = cfg5
+        if world == 1 and not args.batch and args.workload == "qp_diag_n8" and not args.no_other_configs:
+            line["other_configs"] = run_other_configs(L, dev)
         if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (the reference arm covers N>1)
             eng, ckind, a, n, reps = cpu_sample(kind, host0, B, 10.0, args.cpu_sample)
             dt = sum(cpu_pass(eng, kind, a) for _ in range(reps))

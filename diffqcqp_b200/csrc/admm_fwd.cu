@@ -449,6 +449,7 @@ __global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIA
     }
     __syncthreads();  // the records are rewritten by the next batch
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.dense_hint != nullptr) *(volatile int*)(p.dense_hint + 1) = 1;  // this launch has run (launch_admm_fwd)
 }
 
 template <int T, int PROX, int R = T>
@@ -513,18 +514,22 @@ static cudaError_t launch_diag8(const FwdParams& p, cudaStream_t stream) {
 // prox: 0 = x >= 0 (QP), 1 = per-contact disks (QCQP), 2 = box, 3 = box + sign constraint
 // The N == 8 fast paths (thread-per-problem, persistent tiles) are built for diagonal P; a dense batch costs them their flat
 // read of P plus a hand-out of groups inside low-occupancy CTAs (8-15 % slower than the generic kernel, whose 32 warps per
-// SM suit the dense arithmetic).  Whether P is dense is only known on the device, so the kernels report it: they set a
-// flag in page-locked host memory (mapped into the device) when they fall back to the group routine, and the launcher,
-// which reads the flag without synchronising -- it sees the outcome of launches that have completed by now -- sends the
-// next DENSE_HOLD N == 8 launches to the generic kernel, then probes the fast path again.  Results do not depend on the
-// path (bit-identical), so a stale or racy read only costs time.  dq_set_forward_path overrides.
+// SM suit the dense arithmetic).  Whether P is dense is only known on the device, so the kernels report it through two
+// words of page-locked host memory (mapped into the device): hint[0] = 1 when a CTA falls back to the group routine,
+// hint[1] = 1 when the launch's first CTA has finished.  The launcher reads them without synchronising:
+//   FAST     fast path; hint[0] seen -> DENSE
+//   DENSE    generic kernel for `hold` launches, then ONE probe launch on the fast path -> PROBING
+//   PROBING  generic kernel until the probe has reported: dense again -> DENSE with a doubled hold (<= 4096), else FAST
+// (the host may be many launches ahead of the device, so the probe's outcome is waited for, not assumed).  Results do not
+// depend on the path (bit-identical), so a stale or racy read only costs time.  dq_set_forward_path overrides.
 struct DenseHint {
-  int* flag = nullptr;  // page-locked, device-visible at the same address (unified addressing)
-  int hold = 0;         // launches still to be sent to the generic kernel
+  int* flag = nullptr;  // [2] page-locked, device-visible at the same address (unified addressing)
+  int mode = 0;         // 0 FAST, 1 DENSE, 2 PROBING
+  int hold = 0, next_hold = 64;
 };
 static DenseHint g_dense_hint[64];
-constexpr int DENSE_HOLD = 64;
 
+// true: send this launch to the generic kernel.  *flag_out = where a fast-path launch reports (NULL: no reporting).
 static bool n8_batches_look_dense(int dev, cudaStream_t stream, int** flag_out) {
   DenseHint& h = g_dense_hint[dev];
   *flag_out = nullptr;
@@ -534,24 +539,37 @@ static bool n8_batches_look_dense(int dev, cudaStream_t stream, int** flag_out) 
       (void)cudaGetLastError();
       return false;
     }
-    if (cudaHostAlloc((void**)&h.flag, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    if (cudaHostAlloc((void**)&h.flag, 2 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
       (void)cudaGetLastError();
       h.flag = nullptr;
-      *flag_out = nullptr;
       return false;
     }
-    *h.flag = 0;
+    h.flag[0] = h.flag[1] = 0;
   }
+  volatile int* f = h.flag;
   *flag_out = h.flag;
-  if (*(volatile int*)h.flag != 0) {
-    *(volatile int*)h.flag = 0;
-    h.hold = DENSE_HOLD;
+  if (h.mode == 0) {
+    if (f[0] != 0) {
+      h.mode = 1;
+      h.hold = h.next_hold = 64;
+    }
+  } else if (h.mode == 2) {
+    if (f[0] != 0) {  // the probe met dense problems again: back off
+      h.mode = 1;
+      h.next_hold = h.next_hold < 2048 ? 2 * h.next_hold : 4096;
+      h.hold = h.next_hold;
+    } else if (f[1] != 0) {
+      h.mode = 0;
+    }
   }
-  if (h.hold > 0) {
-    --h.hold;
-    return true;
+  if (h.mode == 1) {
+    if (h.hold-- > 0) return true;
+    f[0] = 0;  // the probe: one launch on the fast path, reporting into cleared flags
+    f[1] = 0;
+    h.mode = 2;
+    return false;
   }
-  return false;
+  return h.mode == 2;
 }
 
 cudaError_t launch_admm_fwd(const FwdParams& p_in, int prox, int T, cudaStream_t stream) {

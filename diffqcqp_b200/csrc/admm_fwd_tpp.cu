@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(TPP_BLOCK, TppGeo<E>::CTAS) admm_fwd_tpp8_kern
       solve_group<8, PROX>(p, b0 + 4 * g, b0 + nb, lane, recs + warp * FwdSmem<8>::per_warp_doubles);
       __syncwarp();
     }
+    if (blockIdx.x == 0 && tid == 0 && p.dense_hint != nullptr) *(volatile int*)(p.dense_hint + 1) = 1;  // this launch has run
     return;
   }
 
@@ -889,6 +890,7 @@ __global__ void __launch_bounds__(TPP_BLOCK, TppGeo<E>::CTAS) admm_fwd_tpp8_kern
     }
     TPP_MARK(9, (unsigned long long)ns);
   }
+  if (blockIdx.x == 0 && tid == 0 && p.dense_hint != nullptr) *(volatile int*)(p.dense_hint + 1) = 1;  // this launch has run (launch_admm_fwd)
   TPP_MARK(7, tpp_now());
 }
 

@@ -16,7 +16,7 @@ struct FwdParams {
   const double* vsign;  // SignedBox QP only: v
   const double* warm;   // NULL (the reference's behaviour: warm_start is dead) or the (B,N) start of l_2 (DQ_FLAG_WARM_START)
   double* state;        // nullable (B,N): forward -> backward hand-off: diag(P) of a diagonal problem, NaN for a dense one
-  int* dense_hint;      // nullable, host memory mapped into the device: the N == 8 fast paths set it to 1 when they meet dense P
+  int* dense_hint;      // nullable, [2] ints of host memory mapped into the device: the N == 8 fast paths set [0] when they meet dense P, [1] when the launch has run
   double* x;
   int32_t* iters;  // nullable
   long long B;

@@ -8,6 +8,6 @@ timeout 900 ncu --replay-mode app-range --profile-from-start off --clock-control
 tail -3 gpurun_out/${tag}_ncu.log; head -c 3000 gpurun_out/${tag}_range.csv
 for wl in qcqp_n24 qcqp_n16; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'admm_fwd|_bwd' -s 4 -c 2 -o gpurun_out/${tag}_${wl}_prof -f \
-    python bench.py --workload $wl --batch 65536 --steps 4 --warmup 3 --streams 1 --no-e2e --no-cpu-baseline > gpurun_out/${tag}_${wl}_ncu.log 2>&1
+    python bench.py --workload $wl --batch 65536 --steps 4 --warmup 3 --streams 1 --no-e2e --no-cpu-baseline --no-other-configs > gpurun_out/${tag}_${wl}_ncu.log 2>&1
 done
 ls -la gpurun_out | grep ${tag}
