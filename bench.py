@@ -13,8 +13,8 @@ Timed region (``value``): inputs resident in HBM, K steps over R rotating input 
 footprint exceeds the 126 MB L2 (so no step finds its inputs cached from the previous use), issued
 round-robin on ``--streams`` CUDA streams (default 4: fwd -> bwd of one batch stay ordered, independent
 batches overlap), bracketed by barrier + synchronize, CUDA events on the launching stream (the side
-streams fork from and join into it), max over ranks.  ``config.single_stream_ms_per_step`` is the same
-loop on one stream.
+streams fork from and join into it), max over ranks.  ``detail.single_stream_ms_per_step`` is the same
+loop on one stream.  ``config`` is identical for both arms (common_config).
 ``e2e``: the same metric through the host-buffer C-ABI entry point (dq_qp_solve_host /
 dq_qcqp_solve_host), host->device and device->host copies inside the timed region.
 ``roofline``: the dominant kernel's algorithmic bytes / its measured duration, against the measured

@@ -478,8 +478,8 @@ __global__ void __launch_bounds__(TPP_BLOCK, TppGeo<E>::CTAS) admm_fwd_tpp8_kern
       const int sidx = item / 10;
       e = item - 10 * sidx;
       r = recs + (v ? ul[sidx] : 0) * R::D;
-      const double x0 = r[e < 8 ? R::M + e : (e == 8 ? R::RHO : R::TDK)];
-      const double xs = __dadd_rn(x0, r[R::CADD]);  // P += c I
+      const double x0 = v ? r[e < 8 ? R::M + e : (e == 8 ? R::RHO : R::TDK)] : 1.0;  // (lanes without an item touch no record)
+      const double xs = __dadd_rn(x0, v ? r[R::CADD] : 0.0);  // P += c I
       const double xin = v ? (e < 8 ? xs : x0) : 1.0;
       if (v && e < 8) r[R::M + e] = xin;
       return xin;
@@ -590,7 +590,9 @@ __global__ void __launch_bounds__(TPP_BLOCK, TppGeo<E>::CTAS) admm_fwd_tpp8_kern
       const unsigned um = __ballot_sync(FULL_MASK, need) & G::LEADERS;
       TPP_CLK(c2);
       if (um) {
-        const double tau_inc = rec[R::TAUI], tau_dec = rec[R::TAUD], itd = rec[R::ITD], tdk = rec[R::TDK], itdk = rec[R::ITDK];
+        // (only the slots that update read their record: an idle lane's `rec` may point at a record another slot is rewriting)
+        const double tau_inc = need ? rec[R::TAUI] : 1.0, tau_dec = need ? rec[R::TAUD] : 1.0, itd = need ? rec[R::ITD] : 1.0;
+        const double tdk = need ? rec[R::TDK] : 1.0, itdk = need ? rec[R::ITDK] : 1.0;
         const bool rev = inc ? (rho_up == -1) : (rho_up == 1);  // direction reversal: the taus decay  :94-97 / :108-111
         const bool dk_i = rev && (!QCQP || inc), dk_d = rev && (!QCQP || !inc);  // the QP decays both, the QCQP only the one it uses
         const double n_ti = dk_i ? __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tau_inc, 1))) : tau_inc;

@@ -10,7 +10,9 @@ Devices.  The reference is CPU-only (``.numpy()`` at qcqp.py:30).  Here:
   * CUDA tensors in -> CUDA tensors out, asynchronous on the current stream, no host sync;
   * CPU tensors in (what a user of the reference has) -> inputs are copied to the current CUDA
     device, solved there, and the result is returned as a CPU tensor; device copies are kept on the
-    autograd context so backward only moves ``grad_l`` in and the gradients out.
+    autograd context so backward only moves ``grad_l`` in and the gradients out.  Batches of
+    >= HOST_PIPE_MIN_BATCH problems move through a chunked copy/compute pipeline (copies on side
+    streams overlap the kernels; outputs are pinned CPU tensors).
 There is no CPU compute path: without the CUDA extension or a CUDA device this raises.
 
 Notes carried over from the reference's behaviour:

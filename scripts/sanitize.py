@@ -55,3 +55,32 @@ for path in (0, 1):
         st = torch.empty(300, 8, 1, dtype=torch.float64, device="cuda")
         run(f"hand-off {tag} path={path}", lambda: dq.qp_backward(PP, qd, dq.qp_forward(PP, qd, 1e-7, 300, state=st), torch.ones_like(qd), state=st))
 L.dq_set_forward_path(0)
+
+# the thread-per-problem forward (N == 8, forced: path 3): refill from the queue, shared rho updates, parked problems on
+# tiles (park threshold 5 so that the dump / tile phase is exercised, 0 = never park), every prox, E = 8 and 4, a dense chunk
+P, q, g = wl.qp_diag(700, 8, seed=7)
+Pd, qd = P.cuda(), q.cuda()
+lo, hi, v = -torch.rand_like(qd), torch.rand_like(qd), torch.randn_like(qd)
+Pq, qq, l_n, mu, _ = wl.qcqp_diag(700, 8, seed=8)
+Pm = Pd.clone(); Pm[333] = wl.qp_dense(1, 8, seed=3)[0][0].cuda()
+L.dq_set_forward_path(3)
+for elems in (8, 4):
+    L.dq_set_forward_tuning(2, elems)
+    for cap in (48, 5, 0):
+        L.dq_set_forward_tuning(0, cap)
+        run(f"tpp qp diag E={elems} cap={cap}", lambda: dq.qp_forward(Pd, qd, 1e-7, 500))
+    L.dq_set_forward_tuning(0, 5)
+    run(f"tpp box E={elems}", lambda: dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200))
+    run(f"tpp signed box E={elems}", lambda: dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200, v=v))
+    run(f"tpp qcqp diag E={elems}", lambda: dq.qcqp_forward(Pq.cuda(), qq.cuda(), l_n.cuda(), mu.cuda(), 1e-7, 200))
+    run(f"tpp qp mixed E={elems}", lambda: dq.qp_forward(Pm, qd, 1e-7, 200))
+    st = torch.empty(700, 8, 1, dtype=torch.float64, device="cuda")
+    run(f"tpp hand-off E={elems}", lambda: dq.qp_backward(Pd, qd, dq.qp_forward(Pd, qd, 1e-7, 300, state=st), torch.ones_like(qd), state=st))
+L.dq_set_forward_tuning(0, 48); L.dq_set_forward_tuning(2, 8); L.dq_set_forward_path(0)
+# legacy Box entry point with gamma / dgamma outputs
+import numpy as np
+from diffqcqp_b200 import legacy
+r = np.random.default_rng(0)
+S = r.random((8, 8)); Pn = S @ S.T / 8 + 0.1 * np.eye(8)
+xb = legacy.solveBoxQP(Pn, r.random(8) - 0.5, -0.2 * np.ones(8), 0.2 * np.ones(8), np.zeros(8), 1e-8)
+run("legacy box derivatives", lambda: legacy.solveDerivativesBoxQP(Pn, r.random(8) - 0.5, -0.2 * np.ones(8), 0.2 * np.ones(8), xb, r.random(8)))

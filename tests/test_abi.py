@@ -150,8 +150,13 @@ def test_sass_of_the_persistent_forward_hot_loop():
     import subprocess
     from diffqcqp_b200 import _lib
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
-    if not os.path.exists(cuobjdump):
-        pytest.skip("cuobjdump not available")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cuobjdump) or not os.path.exists(nvcc):
+        pytest.skip("cuobjdump / nvcc not available")
+    # the thresholds below describe what nvcc 12.9 generates; another compiler release may legitimately differ
+    ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout
+    if "release 12.9" not in ver:
+        pytest.skip("SASS regression guard is pinned to nvcc 12.9")
     fun = "_ZN2dq21admm_fwd_diag8_kernelILi0EEEvNS_9FwdParamsE"
     res = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
     m = re.search(fun + r".*?\n\s*REG:(\d+)", res, re.S)
@@ -174,3 +179,27 @@ def test_sass_of_the_persistent_forward_hot_loop():
         assert any("VOTE" in t for t in body) and any("DSETP" in t for t in body)
         assert not any("BRA.DIV" in t for t in body), "divergence guards inside the persistent forward's loop"
         assert not any(t.startswith(("LDL", "STL")) or " LDL" in t or " STL" in t for t in body), "spills inside the loop"
+
+
+def test_sass_of_the_thread_per_problem_forward():
+    """The round-2 headline kernel (admm_fwd_tpp8_kernel<PROX_NONNEG, 8>): present in the code object, within the register
+    budget of three CTAs per SM, no spills, and its main loop carries the branch-free double-precision seeds
+    (MUFU.RSQ64H / MUFU.RCP64H) of fast_sqrt / fast_rcp."""
+    import re
+    import shutil
+    import subprocess
+    from diffqcqp_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cuobjdump) or not os.path.exists(nvcc):
+        pytest.skip("cuobjdump / nvcc not available")
+    if "release 12.9" not in subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout:
+        pytest.skip("SASS regression guard is pinned to nvcc 12.9")
+    fun = "_ZN2dq20admm_fwd_tpp8_kernelILi0ELi8EEEvNS_9FwdParamsEi"
+    res = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    m = re.search(fun + r".*?\n\s*REG:(\d+)\s+STACK:(\d+)", res, re.S)
+    assert m, "kernel missing from the code object"
+    assert int(m.group(1)) <= 168 and int(m.group(2)) == 0, (m.group(1), m.group(2))
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", fun, _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "MUFU.RSQ64H" in sass and "MUFU.RCP64H" in sass and "ATOMS" in sass
+    assert not re.search(r"\b(LDL|STL)\b", sass), "local-memory traffic in the thread-per-problem forward"
