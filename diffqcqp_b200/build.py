@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiffqcqp_b200.so")
-SOURCES = ["admm_fwd.cu", "admm_fwd_tpp.cu", "qp_bwd.cu", "qcqp_bwd.cu", "boxqp_bwd.cu", "api.cu"]
+SOURCES = ["admm_fwd.cu", "admm_fwd_tpp.cu", "qp_bwd.cu", "qcqp_bwd.cu", "boxqp_bwd.cu", "large_n.cu", "api.cu"]
 HEADERS = ["common.cuh", "kernels.h", "admm_fwd_group.cuh", os.path.join("..", "..", "include", "diffqcqp_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

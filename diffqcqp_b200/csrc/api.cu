@@ -52,6 +52,8 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
     if (!aligned8(l_n) || !aligned8(mu)) return DQ_ERR_ALIGN;
   }
   if (B == 0) return DQ_OK;
+  const bool large = N > DQ_MAX_N_TILE;  // a warp per problem out of a global-memory workspace (csrc/large_n.cu)
+  if (large && warm) return DQ_ERR_UNSUPPORTED_N;
   const int T = dq::tile_width(N);
   const int G = 32 / T;
   dq::FwdParams p;
@@ -64,7 +66,7 @@ int forward_impl(bool qcqp, const double* P, const double* q, const double* l_n,
   p.adaptive = (adaptive & DQ_FLAG_ADAPTIVE_RHO) ? 1 : 0;
   p.n_groups = (B + G - 1) / G;
   const int prox = qcqp ? 1 : (l_min ? (v ? 3 : 2) : 0);
-  cudaError_t e = dq::launch_admm_fwd(p, prox, T, stream);
+  cudaError_t e = large ? dq::launch_large_fwd(p, prox, stream) : dq::launch_admm_fwd(p, prox, T, stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DQ_OK;
@@ -94,7 +96,9 @@ int backward_impl(bool qcqp, const double* P, const double* q, const double* l_n
   p.state = aligned8(state) ? state : nullptr;
   p.B = B; p.N = N;
   p.n_groups = (B + G - 1) / G;
-  cudaError_t e = qcqp ? dq::launch_qcqp_bwd(p, T, stream) : dq::launch_qp_bwd(p, T, stream);
+  cudaError_t e;
+  if (N > DQ_MAX_N_TILE) e = qcqp ? dq::launch_large_qcqp_bwd(p, stream) : dq::launch_large_qp_bwd(p, stream);
+  else e = qcqp ? dq::launch_qcqp_bwd(p, T, stream) : dq::launch_qp_bwd(p, T, stream);
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return DQ_OK;
@@ -407,7 +411,7 @@ const char* dq_error_string(int code) {
   switch (code) {
     case DQ_OK: return "ok";
     case DQ_ERR_BAD_ARG: return "bad argument (null pointer, negative batch, N < 1, or odd N for the QCQP)";
-    case DQ_ERR_UNSUPPORTED_N: return "N exceeds DQ_MAX_N (one problem must fit one warp tile)";
+    case DQ_ERR_UNSUPPORTED_N: return "N exceeds DQ_MAX_N = 128 (or DQ_MAX_N_TILE = 32 for the Box backward / the warm-start extension)";
     case DQ_ERR_ALIGN: return "pointer is not 8-byte aligned";
     case DQ_ERR_CUDA: return "CUDA runtime error (see dq_last_cuda_error)";
     default: return "unknown error code";
@@ -482,6 +486,7 @@ int dq_boxqp_backward_ex(const double* P, const double* q, const double* l_min, 
   if (!aligned8(grad_x) || !aligned8(l_min) || !aligned8(l_max) || !aligned8(grad_P) || !aligned8(grad_q) ||
       !aligned8(grad_l_min) || !aligned8(grad_l_max) || !aligned8(gamma) || !aligned8(dgamma))
     return DQ_ERR_ALIGN;
+  if (N > DQ_MAX_N_TILE) return DQ_ERR_UNSUPPORTED_N;  // the Box backward exists as a tile kernel only
   if (B == 0 || (!grad_P && !grad_q && !grad_l_min && !grad_l_max && !gamma && !dgamma)) return DQ_OK;
   const int T = dq::tile_width(N);
   const int G = 32 / T;

@@ -82,5 +82,9 @@ cudaError_t launch_selftest_inverse(const double* x, long long n, unsigned long 
 cudaError_t launch_qp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_qcqp_bwd(const BwdParams& p, int T, cudaStream_t stream);
 cudaError_t launch_boxqp_bwd(const BoxBwdParams& p, int T, cudaStream_t stream);
+// 32 < N <= 128 (large_n.cu): one warp per problem, matrices in a stream-ordered global-memory workspace
+cudaError_t launch_large_fwd(const FwdParams& p, int prox, cudaStream_t stream);
+cudaError_t launch_large_qp_bwd(const BwdParams& p, cudaStream_t stream);
+cudaError_t launch_large_qcqp_bwd(const BwdParams& p, cudaStream_t stream);
 
 }  // namespace dq

@@ -106,7 +106,7 @@ def _compute_device(*tensors) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-MAX_N = 32  # DQ_MAX_N of include/diffqcqp_b200.h (dq_max_n())
+MAX_N = 128  # DQ_MAX_N of include/diffqcqp_b200.h (dq_max_n()); N <= 32 runs the warp-tile kernels, above that a slow warp-per-problem path
 
 
 def _check_shapes(P, q, l_n=None, mu=None):
@@ -114,8 +114,8 @@ def _check_shapes(P, q, l_n=None, mu=None):
         raise ValueError(f"P must have shape (B,N,N), got {tuple(P.shape)}")
     B, N = P.size(0), P.size(1)
     if N > MAX_N:
-        raise ValueError(f"N={N} exceeds the {MAX_N} unknowns per problem these kernels support (one problem per warp tile: "
-                         f"QPs up to N={MAX_N}, QCQPs up to {MAX_N // 2} contacts); the reference's solveQP / solveQCQP have no such limit")
+        raise ValueError(f"N={N} exceeds the {MAX_N} unknowns per problem these kernels support (QPs up to N={MAX_N}, QCQPs up to "
+                         f"{MAX_N // 2} contacts); the reference's solveQP / solveQCQP have no such limit")
     if q.dim() != 3 or tuple(q.shape) != (B, N, 1):
         raise ValueError(f"q must have shape (B,N,1)=({B},{N},1), got {tuple(q.shape)}")
     if l_n is not None:

@@ -35,11 +35,13 @@ extern "C" {
 
 #define DQ_OK 0
 #define DQ_ERR_BAD_ARG 1      /* null required pointer, B < 0, N < 1, odd N for the QCQP, ...      */
-#define DQ_ERR_UNSUPPORTED_N 2 /* N above DQ_MAX_N                                                 */
+#define DQ_ERR_UNSUPPORTED_N 2 /* N above DQ_MAX_N (or above DQ_MAX_N_TILE where only the tile kernels exist) */
 #define DQ_ERR_ALIGN 3        /* pointer not 8-byte aligned                                       */
 #define DQ_ERR_CUDA 4         /* CUDA runtime error; dq_last_cuda_error() has the code            */
 
-#define DQ_MAX_N 32           /* one problem lives in one warp tile: N <= 32 (QCQP: <= 16 contacts) */
+#define DQ_MAX_N 128          /* N <= 128 (QCQP: <= 64 contacts).  Up to DQ_MAX_N_TILE a problem lives in one warp tile  */
+#define DQ_MAX_N_TILE 32      /* (the fast kernels); above it a warp solves it out of a global-memory workspace (slow    */
+                              /* capability path; no Box backward, no warm-start extension there: DQ_ERR_UNSUPPORTED_N)   */
 
 /* Library / build identification. */
 int dq_version(void);                 /* 10000*major + 100*minor + patch                          */

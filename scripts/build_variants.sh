@@ -7,7 +7,7 @@ mkdir -p scripts/variants/obj
 for spec in "$@"; do
   name=${spec%%=*}; flags=${spec#*=}
   objs=""
-  for f in admm_fwd admm_fwd_tpp qp_bwd qcqp_bwd boxqp_bwd api; do
+  for f in admm_fwd admm_fwd_tpp qp_bwd qcqp_bwd boxqp_bwd large_n api; do
     o=scripts/variants/obj/${name}_$f.o
     nvcc $flags -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -c diffqcqp_b200/csrc/$f.cu -o $o &
     objs="$objs $o"

@@ -84,3 +84,13 @@ r = np.random.default_rng(0)
 S = r.random((8, 8)); Pn = S @ S.T / 8 + 0.1 * np.eye(8)
 xb = legacy.solveBoxQP(Pn, r.random(8) - 0.5, -0.2 * np.ones(8), 0.2 * np.ones(8), np.zeros(8), 1e-8)
 run("legacy box derivatives", lambda: legacy.solveDerivativesBoxQP(Pn, r.random(8) - 0.5, -0.2 * np.ones(8), 0.2 * np.ones(8), xb, r.random(8)))
+# 32 < N <= 128: the warp-per-problem path (csrc/large_n.cu)
+for N, B in ((40, 9), (64, 5)):
+    P, q, g = wl.qp_dense(B, N, seed=N)
+    Pd, qd, gd = P.cuda(), q.cuda(), g.cuda()
+    run(f"large-N qp N={N}", lambda: dq.qp_backward(Pd, qd, dq.qp_forward(Pd, qd, 1e-7, 200), gd))
+    lo, hi, v = -torch.rand_like(qd), torch.rand_like(qd), torch.randn_like(qd)
+    run(f"large-N signed box N={N}", lambda: dq.boxqp_forward(Pd, qd, lo, hi, 1e-7, 200, v=v))
+    P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=N)
+    a = [t.cuda() for t in (P, q, l_n, mu)]
+    run(f"large-N qcqp N={N}", lambda: dq.qcqp_backward(*a, dq.qcqp_forward(*a, 1e-7, 200), g.cuda()))

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_identification(lib):
     assert lib.dq_build_arch() == b"sm_100a"
     assert lib.dq_version() >= 100
-    assert lib.dq_max_n() == 32
+    assert lib.dq_max_n() == 128
     assert lib.dq_error_string(0) == b"ok"
     for code in (1, 2, 3, 4):
         assert len(lib.dq_error_string(code)) > 3
@@ -72,13 +72,14 @@ def test_argument_validation_without_gpu(lib):
     assert lib.dq_qp_forward(None, p, None, p, None, 4, 8, 1e-7, 1e-7, 10, 1, None) == BAD
     assert lib.dq_qp_forward(p, p, None, p, None, -1, 8, 1e-7, 1e-7, 10, 1, None) == BAD
     assert lib.dq_qp_forward(p, p, None, p, None, 4, 0, 1e-7, 1e-7, 10, 1, None) == BAD
-    assert lib.dq_qp_forward(p, p, None, p, None, 4, 33, 1e-7, 1e-7, 10, 1, None) == UNSUP
+    assert lib.dq_qp_forward(p, p, None, p, None, 4, 129, 1e-7, 1e-7, 10, 1, None) == UNSUP
+    assert lib.dq_qp_forward(p, p, p, p, None, 4, 33, 1e-7, 1e-7, 10, 3, None) == UNSUP  # warm-start extension: tile kernels only
     assert lib.dq_qp_forward(p + 4, p, None, p, None, 4, 8, 1e-7, 1e-7, 10, 1, None) == ALIGN
     assert lib.dq_qcqp_forward(p, p, p, p, None, p, None, 4, 7, 1e-7, 1e-7, 10, 1, None) == BAD  # odd N
     assert lib.dq_qcqp_forward(p, p, None, p, None, p, None, 4, 8, 1e-7, 1e-7, 10, 1, None) == BAD
     assert lib.dq_qp_backward(p, p, p, None, p, p, 4, 8, None) == BAD
     assert lib.dq_qcqp_backward(p, p, p, p, p, p, p, p, p, p, 4, 9, None) == BAD
-    assert lib.dq_qp_solve_host(p, p, p, None, None, None, 4, 40, 1e-7, 1e-7, 10, -1) == UNSUP
+    assert lib.dq_qp_solve_host(p, p, p, None, None, None, 4, 140, 1e-7, 1e-7, 10, -1) == UNSUP
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -502,9 +502,11 @@ def test_edge_sizes_and_layouts(dq, wl, oracle):
         x, it = dq.qcqp_forward(*dev(P, q, l_n, mu), EPS, 1000, return_iters=True)
         assert np.array_equal(it.cpu().numpy(), ito), (N, B)
         check_x(x, xo, EPS)
-    # N above the tile limit is rejected, not mis-solved
+    # N above DQ_MAX_N is rejected, not mis-solved
     with pytest.raises(Exception):
-        dq.qp_forward(torch.eye(33, dtype=torch.float64, device="cuda")[None], torch.ones(1, 33, 1, dtype=torch.float64, device="cuda"), EPS, 10)
+        dq.qp_forward(torch.eye(129, dtype=torch.float64, device="cuda")[None], torch.ones(1, 129, 1, dtype=torch.float64, device="cuda"), EPS, 10)
+    with pytest.raises(ValueError):
+        qcqp.QPFn2.apply(torch.eye(129, dtype=torch.float64)[None], torch.ones(1, 129, 1, dtype=torch.float64), None, EPS, 10)
     # non-contiguous P (a transposed view of a symmetric batch) and float32 inputs
     P, q, g = wl.qp_dense(50, 8, seed=99)
     x_ref = qcqp.QPFn2.apply(P.cuda(), q.cuda(), torch.zeros_like(q).cuda(), EPS, 1000)
@@ -1043,3 +1045,69 @@ def test_fast_sqrt_rcp_are_the_library_bits(cuda_lib):
         report(f"fast sqrt/rcp self-test n={xs.numel()}: mismatches sqrt {b[0]} rcp {b[1]} rcp(sqrt) {b[2]}; outside the fast range {b[3]}")
         assert b[:3] == [0, 0, 0], b
     assert b[3] >= 7
+
+
+# ------------------------------------------------------------------------------------ 32 < N <= 128: the warp-per-problem path
+@pytest.mark.parametrize("N,B", [(33, 70), (40, 64), (64, 48), (96, 13), (128, 9)])
+def test_large_n_qp_forward_backward_vs_oracle(dq, wl, oracle, N, B):
+    """Problems too large for a warp tile (csrc/large_n.cu: a warp per problem, matrices in a global-memory workspace):
+    same bars as the tile kernels -- x within 10*eps of the oracle, iteration counts equal, QP gradient rows to 1e-9."""
+    P, q, g = wl.qp_dense(B, N, seed=1200 + N)
+    xo, ito = oracle.qp_forward(P.numpy(), q.numpy(), None, EPS, 1000, return_iters=True)
+    x, it = dq.qp_forward(*dev(P, q), EPS, 1000, return_iters=True)
+    mism = int((it.cpu().numpy() != ito).sum())
+    check_x(x, xo, EPS)
+    report(f"large-N qp_dense B={B} N={N}: iteration-count mismatches {mism}/{B}; {x_stats(x, xo, EPS)}")
+    assert mism <= max(1, B // 50)
+    gPo, gqo = oracle.qp_backward(P.numpy(), q.numpy(), xo, g.numpy())
+    gP, gq = dq.qp_backward(*dev(P, q), torch.from_numpy(xo).cuda(), g.cuda())
+    assert rel_rows(gq, gqo).max() <= 1e-9 and rel_rows(gP, gPo).max() <= 1e-9
+    # diagonal P, Box and SignedBox prox on the same path
+    Pd_, qd_, _ = wl.qp_diag(B, N, seed=1300 + N)
+    xo = oracle.qp_forward(Pd_.numpy(), qd_.numpy(), None, EPS, 1000)
+    check_x(dq.qp_forward(*dev(Pd_, qd_), EPS, 1000), xo, EPS)
+    gen = torch.Generator().manual_seed(N)
+    lo = -torch.rand(B, N, 1, generator=gen, dtype=torch.float64)
+    hi = torch.rand(B, N, 1, generator=gen, dtype=torch.float64)
+    v = 2 * torch.rand(B, N, 1, generator=gen, dtype=torch.float64) - 1
+    xo = oracle.boxqp_forward(P.numpy(), q.numpy(), lo.numpy(), hi.numpy(), EPS, 1000)
+    check_x(dq.boxqp_forward(*dev(P, q, lo, hi), EPS, 1000), xo, EPS)
+    xo = oracle.boxqp_forward(P.numpy(), q.numpy(), lo.numpy(), hi.numpy(), EPS, 1000, v=v.numpy())
+    check_x(dq.boxqp_forward(*dev(P, q, lo, hi), EPS, 1000, v=v.cuda()), xo, EPS)
+
+
+@pytest.mark.parametrize("N,B", [(34, 40), (48, 32), (64, 24), (128, 6)])
+def test_large_n_qcqp_forward_backward_vs_oracle(dq, wl, oracle, N, B):
+    """QCQP above the tile limit (17 .. 64 contacts): forward as above; gradients to the refinement-iterate bar of DESIGN.md
+    section 4 (every row matches one of the oracle's iterates 1..5; median distance to its own choice <= 1e-8)."""
+    import qcqp
+    P, q, l_n, mu, g = wl.qcqp_dense(B, N, seed=1400 + N)
+    xo, ito = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, EPS, 1000, return_iters=True)
+    d = dev(P, q, l_n, mu)
+    x, it = dq.qcqp_forward(*d, EPS, 1000, return_iters=True)
+    mism = int((it.cpu().numpy() != ito).sum())
+    check_x(x, xo, EPS)
+    report(f"large-N qcqp_dense B={B} N={N}: iteration-count mismatches {mism}/{B}; {x_stats(x, xo, EPS)}")
+    assert mism <= max(1, B // 20)
+    go = oracle.qcqp_backward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), xo, g.numpy())
+    cands = []
+    try:
+        for k in (1, 2, 3, 4, 5):
+            oracle.set_ir_force(k)
+            cands.append(oracle.qcqp_backward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), xo, g.numpy()))
+    finally:
+        oracle.set_ir_force(0)
+    gg = dq.qcqp_backward(*d, torch.from_numpy(xo).cuda(), g.cuda())
+    for i, name in enumerate(("grad_P", "grad_q", "grad_l_n", "grad_mu")):
+        got = gg[i].cpu().numpy()
+        assert np.all(np.isfinite(got)), name
+        r_best = np.stack([rel_rows(got, c[i]) for c in cands]).min(0)
+        tol = 1e-5 if i < 2 else 1e-3
+        assert r_best.max() <= tol, (name, N, r_best.max())
+        assert np.median(rel_rows(got, go[i])) <= 1e-7, (name, N, np.median(rel_rows(got, go[i])))
+    # through the layer, CPU tensors in
+    leaves = [a.clone().requires_grad_(True) for a in (P, q, l_n, mu)]
+    xl = qcqp.QCQPFn2.apply(*leaves, torch.zeros_like(q), EPS, 1000)
+    assert torch.equal(xl.detach(), x.cpu())
+    (xl * g).sum().backward()
+    assert all(a.grad is not None and torch.all(torch.isfinite(a.grad)) for a in leaves)
