@@ -600,6 +600,7 @@ __global__ void __launch_bounds__(TPP_BLOCK, TppGeo<E>::CTAS) admm_fwd_tpp8_kern
         const double n_tdk = dk_d ? __dadd_rn(1, __dmul_rn(.8, __dsub_rn(tdk, 1))) : tdk;
         const double c = __dmul_rn(rho, __dsub_rn(inc ? n_ti : n_itd, 1));               // :98 / :557, :112 / :571
         const double n_rho = inc ? __dmul_rn(rho, n_ti) : div_by(rho, n_td, n_itd);     // rho *= tau_inc | rho /= tau_dec
+        __syncwarp();  // every lane's reads of its slot's record (above, and in take()) come before the leader's writes
         if (need) {
           rho = n_rho;
           rho_up = inc ? 1 : -1;

@@ -283,6 +283,7 @@ __device__ void w_refine(double* A, const double* dd, double* AA, double* AAi, d
       r2 = fma(d, d, r2);
     }
     const double res = sqrt(warp_sum(r2));  // :31
+    __syncwarp();                           // t is rewritten by the next step's product
     if (res_pred - res < EPS_IR) {
       ni++;
     } else {
