@@ -823,7 +823,12 @@ def run_b200_arm(args):
         peak, peak_src = hbm_peak()
         # launch_admm_fwd's dispatch (csrc/admm_fwd.cu): N == 8 QPs -> thread-per-problem kernel from 65536 problems, the
         # persistent tile kernel below that; everything else the generic kernel
-        fwd_name = ("admm_fwd_tpp8_kernel" if B >= 65536 else "admm_fwd_diag8_kernel") if (kind == "qp" and N == 8) else "admm_fwd_kernel"
+        if N == 8 and B >= 65536:
+            fwd_name = "admm_fwd_tpp8_kernel"
+        elif N == 8 and kind == "qp":
+            fwd_name = "admm_fwd_diag8_kernel"
+        else:
+            fwd_name = "admm_fwd_kernel"
         sm_mhz = (clocks or {}).get("sm_mhz")
         dom = fwd_name if fwd_avg >= bwd_avg else ("qp_bwd_kernel" if kind == "qp" else "qcqp_bwd_kernel")
         dom_ms = max(fwd_avg, bwd_avg)

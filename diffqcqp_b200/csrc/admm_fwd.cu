@@ -584,8 +584,7 @@ cudaError_t launch_admm_fwd(const FwdParams& p_in, int prox, int T, cudaStream_t
   }
   // N == 8, large batches: one problem per thread (admm_fwd_tpp.cu) -- 2.4x fewer instructions per solve than the tile
   // kernels, but a lane owns a whole problem, so it needs >= ~1 problem per thread slot of the device to pay
-  if (n8 && (g_fwd_path == 3 || (g_fwd_path == 0 && p.B >= g_tpp_min_batch && prox != PROX_DISK)))
-    return launch_tpp8(p, prox, stream);
+  if (n8 && (g_fwd_path == 3 || (g_fwd_path == 0 && p.B >= g_tpp_min_batch))) return launch_tpp8(p, prox, stream);
   if (g_fwd_path != 1 && n8 && (prox != PROX_DISK || g_fwd_path == 2)) {  // (warm-started batches: generic kernel; their iteration counts are short and even)
     switch (prox) {
       case PROX_NONNEG: return launch_diag8<PROX_NONNEG>(p, stream);

@@ -933,10 +933,13 @@ int set_tpp_cap_it(int v) {
   return old;
 }
 
-static int g_tpp_elems = 8;  // elements per lane: 8 or 4 (dq_set_forward_tuning key 2)
+// elements per lane: 8 or 4, 0 = automatic (dq_set_forward_tuning key 2).  Automatic: 8 for the QP / Box prox; 4 for the disk
+// prox, whose iteration carries four square roots and eight divisions per problem -- a lane pair halves that chain per lane
+// (B = 65536 diagonal QCQPs: 81 us per overlapped launch and 106 us isolated at E = 4, 85 / 131 at E = 8, generic kernel 97 / 121).
+static int g_tpp_elems = 0;
 int set_tpp_elems(int e) {
   const int old = g_tpp_elems;
-  if (e == 8 || e == 4) g_tpp_elems = e;
+  if (e == 8 || e == 4 || e == 0) g_tpp_elems = e;
   return old;
 }
 
@@ -968,10 +971,8 @@ static cudaError_t launch_tpp8_t(const FwdParams& p, cudaStream_t stream) {
 
 template <int PROX>
 static cudaError_t launch_tpp8_p(const FwdParams& p, cudaStream_t stream) {
-  switch (g_tpp_elems) {
-    case 4: return launch_tpp8_t<PROX, 4>(p, stream);
-    default: return launch_tpp8_t<PROX, 8>(p, stream);
-  }
+  const int e = g_tpp_elems != 0 ? g_tpp_elems : (PROX == PROX_DISK ? 4 : 8);
+  return e == 4 ? launch_tpp8_t<PROX, 4>(p, stream) : launch_tpp8_t<PROX, 8>(p, stream);
 }
 
 cudaError_t launch_tpp8(const FwdParams& p, int prox, cudaStream_t stream) {

@@ -75,7 +75,7 @@ int set_fwd_path(int path);  // 0 = automatic, 1 = generic kernel, 2 = persisten
 // N == 8, 32-byte aligned P, no warm start: one problem per thread (admm_fwd_tpp.cu)
 cudaError_t launch_tpp8(const FwdParams& p, int prox, cudaStream_t stream);
 long long set_tpp_min_batch(long long b);  // automatic path: smallest batch that takes the thread-per-problem kernel; returns the previous value
-int set_tpp_elems(int e);  // elements of a problem per lane in the thread-per-problem kernel: 8 (default) or 4; returns the previous value
+int set_tpp_elems(int e);  // elements of a problem per lane in the thread-per-problem kernel: 8, 4 or 0 = automatic (default); returns the previous value
 int set_tpp_cap_it(int v);  // iterations after which the thread-per-problem kernel parks a problem for its tile phase; returns the previous value
 // bad[0..2] += mismatches of fast_sqrt / fast_rcp / fast_rcp(fast_sqrt) against the library's, bad[3] += values outside the fast range
 cudaError_t launch_selftest_inverse(const double* x, long long n, unsigned long long* bad, cudaStream_t stream);

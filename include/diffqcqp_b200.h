@@ -190,7 +190,7 @@ int64_t dq_launch_count(void);
 
 /*
  * Forward kernel selection (process-wide; for tests and A/B timing).  0 = automatic: at N == 8 with a 32-byte aligned P
- * and no warm start, batches of >= 65536 QP / Box QP problems run the thread-per-problem kernel (one problem per thread,
+ * and no warm start, batches of >= 65536 problems (QP, Box QP, QCQP) run the thread-per-problem kernel (one problem per thread,
  * stragglers finished on 8-lane tiles), smaller ones the persistent-CTA tile kernel (diagonal batches on refilled tile
  * slots); everything else the generic kernel.  1 = generic kernel only.  2 = persistent tile kernel wherever it applies
  * (also the QCQP at N == 8).  3 = thread-per-problem kernel wherever it applies (also the QCQP at N == 8, any batch size).
@@ -203,7 +203,8 @@ int dq_set_forward_path(int path);
  *   key 0: iterations after which the thread-per-problem kernel parks a still-running problem for its tile phase
  *          (default 48; 0 = never)
  *   key 1: smallest batch the automatic path gives to the thread-per-problem kernel (default 65536)
- *   key 2: elements of a problem each lane of that kernel holds: 8 (one thread per problem) or 4 (a lane pair)
+ *   key 2: elements of a problem each lane of that kernel holds: 8 (one thread per problem), 4 (a lane pair), 0 = automatic
+ *          (default: 8 for the QP / Box QP, 4 for the QCQP)
  * Returns the previous value, -1 for an unknown key.
  */
 int64_t dq_set_forward_tuning(int32_t key, int64_t value);

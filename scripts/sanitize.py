@@ -76,7 +76,7 @@ for elems in (8, 4):
     run(f"tpp qp mixed E={elems}", lambda: dq.qp_forward(Pm, qd, 1e-7, 200))
     st = torch.empty(700, 8, 1, dtype=torch.float64, device="cuda")
     run(f"tpp hand-off E={elems}", lambda: dq.qp_backward(Pd, qd, dq.qp_forward(Pd, qd, 1e-7, 300, state=st), torch.ones_like(qd), state=st))
-L.dq_set_forward_tuning(0, 48); L.dq_set_forward_tuning(2, 8); L.dq_set_forward_path(0)
+L.dq_set_forward_tuning(0, 48); L.dq_set_forward_tuning(2, 0); L.dq_set_forward_path(0)
 # legacy Box entry point with gamma / dgamma outputs
 import numpy as np
 from diffqcqp_b200 import legacy

@@ -78,4 +78,4 @@ for B in [int(b) for b in a.batches.split(",")]:
               f"4-stream us/launch {e0.elapsed_time(e1) * 1e3 / 400:.1f}", flush=True)
     L.dq_set_forward_path(0)
     L.dq_set_forward_tuning(0, 48)
-    L.dq_set_forward_tuning(2, 8)
+    L.dq_set_forward_tuning(2, 0)

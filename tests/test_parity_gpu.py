@@ -799,6 +799,7 @@ def test_forward_paths_bit_identical_qp(dq, wl, cuda_lib, B):
             cuda_lib.dq_set_forward_tuning(2, old_e)
     finally:
         cuda_lib.dq_set_forward_path(0)
+        cuda_lib.dq_set_forward_tuning(2, 0)
     assert torch.equal(it0, it1)
     assert torch.equal(x0.view(torch.int64), x1.view(torch.int64))
     for name, xx, ii in res:
