@@ -28,8 +28,11 @@ __device__ __forceinline__ double tile_sum(double v) {
 // identity.  Lane i enters with a[0..i] = lower-triangular part of row i of M (a[i] = diagonal) and
 // leaves with out[0..T) = row i of M^{-1} (= column i, M^{-1} is symmetric).
 //
-// Lb   : this tile's T x T shared scratch (row stride T).  Entries with an index >= N must be zero
-//        on entry and are never written, so padded lanes/columns drop out of every sum.
+// Lb   : this tile's T-row shared scratch, row stride S doubles (S >= T, even).  Entries with an index >= N must be
+//        zero on entry and are never written, so padded lanes/columns drop out of every sum.  S = T makes the
+//        column store Lb[ti][k] a T-way bank conflict (rows 8 T bytes apart: 18 wavefronts per store at T = 16, a
+//        fifth of all shared-memory wavefronts of the N = 16 forward, profiles/r02_qcqp_n16_ncu_lines.txt); S = T + 2
+//        spreads the rows over the banks (2-way at T = 16, 4-way at T = 32) and keeps rows 16-byte aligned.
 // dinv : this tile's T-entry shared scratch for the reciprocal pivots (entries >= N zero).
 // The factor is stored symmetrically (Lb[i][k] = Lb[k][i] = L(i,k)) so both substitutions read rows,
 // all lanes the same address (shared-memory broadcast), vectorisable to 128-bit loads.
@@ -42,7 +45,7 @@ __device__ __forceinline__ double tile_sum(double v) {
 // R <= T is the row capacity the loops are unrolled to (N <= R): a 32-lane tile with N <= 24 runs the R = 24 instance,
 // 44 % fewer unrolled triangular-loop instructions and 16 fewer registers per array (the T = 32 forward is
 // instruction-fetch bound, profiles/r01_qcqp_n24_ncu_lines.txt: no_inst 37 % of the stall samples).
-template <int T, int R = T>
+template <int T, int R = T, int S = T>
 __device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R], double* Lb, double* dinv,
                                                  int N, int ti, int tile_base_lane) {
   // ---- Cholesky, left-looking, one column per step (Eigen LLT unblocked order)
@@ -52,18 +55,18 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
       for (int j = 0; j + 1 < k; j += 2) {
-        acc0 = fma(a[j], Lb[k * T + j], acc0);
-        acc1 = fma(a[j + 1], Lb[k * T + j + 1], acc1);
+        acc0 = fma(a[j], Lb[k * S + j], acc0);
+        acc1 = fma(a[j + 1], Lb[k * S + j + 1], acc1);
       }
-      if (k & 1) acc0 = fma(a[k - 1], Lb[k * T + k - 1], acc0);
+      if (k & 1) acc0 = fma(a[k - 1], Lb[k * S + k - 1], acc0);
       const double s = a[k] - (acc0 + acc1);
       const double skk = __shfl_sync(FULL_MASK, s, tile_base_lane + k);
       const double rp = rsqrt(skk);                        // 1 / L(k,k)
       const double val = (ti == k) ? skk * rp : s * rp;    // L(k,k) = sqrt(pivot);  L(i,k) = s / L(k,k)
       a[k] = val;
       if (ti >= k && ti < N) {
-        Lb[ti * T + k] = val;
-        Lb[k * T + ti] = val;
+        Lb[ti * S + k] = val;
+        Lb[k * S + ti] = val;
       }
       if (ti == k) dinv[k] = rp;
       __syncwarp();
@@ -76,10 +79,10 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R
       double acc0 = (i == ti) ? 1.0 : 0.0, acc1 = 0.0;
 #pragma unroll
       for (int j = 0; j + 1 < i; j += 2) {
-        acc0 = fma(-Lb[i * T + j], out[j], acc0);
-        acc1 = fma(-Lb[i * T + j + 1], out[j + 1], acc1);
+        acc0 = fma(-Lb[i * S + j], out[j], acc0);
+        acc1 = fma(-Lb[i * S + j + 1], out[j + 1], acc1);
       }
-      if (i & 1) acc0 = fma(-Lb[i * T + i - 1], out[i - 1], acc0);
+      if (i & 1) acc0 = fma(-Lb[i * S + i - 1], out[i - 1], acc0);
       out[i] = (acc0 + acc1) * dinv[i];
     } else {
       out[i] = 0.0;
@@ -92,10 +95,10 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
       for (int j = i + 1; j + 1 < R; j += 2) {
-        acc0 = fma(Lb[i * T + j], out[j], acc0);
-        acc1 = fma(Lb[i * T + j + 1], out[j + 1], acc1);
+        acc0 = fma(Lb[i * S + j], out[j], acc0);
+        acc1 = fma(Lb[i * S + j + 1], out[j + 1], acc1);
       }
-      if ((R - 1 - i) & 1) acc0 = fma(Lb[i * T + R - 1], out[R - 1], acc0);
+      if ((R - 1 - i) & 1) acc0 = fma(Lb[i * S + R - 1], out[R - 1], acc0);
       out[i] = (out[i] - (acc0 + acc1)) * dinv[i];
     }
   }

@@ -21,12 +21,17 @@
 
 namespace dq {
 
+#ifndef DQ_BWD_PAD
+#define DQ_BWD_PAD 2  // padding of the [T][T] scratch rows, doubles (0: the round-1 layout, for A/B builds)
+#endif
 template <int T>
 struct BwdQcqpSmem {
   static constexpr int WS = T / 2 + 1;  // padded row stride of the L21 scratch
+  static constexpr int S = T + DQ_BWD_PAD;  // row stride of the two [T][T] scratch matrices: rows spread over the banks, so a lane's row
+                                            // store and tile_spd_inverse's column store stop being T-way bank conflicts
   static constexpr int WARPS = (T == 8) ? 4 : 2;  // warps per CTA (independent; no CTA-level barrier)
-  // per warp: Lbuf 32*T, Dbuf 32*T, Wbuf 32*WS (+pad to even), vbuf 32, dinv 32, cbuf 4*32 (contact broadcast), dlb 32, xb 32
-  static constexpr int per_warp_doubles = 2 * 32 * T + ((32 * WS + 1) & ~1) + 32 + 32 + 4 * 32 + 32 + 32;
+  // per warp: Lbuf 32*S, Dbuf 32*S, Wbuf 32*WS (+pad to even), vbuf 32, dinv 32, cbuf 4*32 (contact broadcast), dlb 32, xb 32
+  static constexpr int per_warp_doubles = 2 * 32 * S + ((32 * WS + 1) & ~1) + 32 + 32 + 4 * 32 + 32 + 32;
   static constexpr size_t bytes = (size_t)WARPS * per_warp_doubles * sizeof(double);
 };
 
@@ -42,6 +47,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
   constexpr int T2 = T / 2;
   constexpr int R2 = R / 2;
   constexpr int WS = BwdQcqpSmem<T>::WS;
+  constexpr int S = BwdQcqpSmem<T>::S;
   constexpr int WARPS = BwdQcqpSmem<T>::WARPS;
   constexpr double MU_IR = 1e-7, EPS_IR = 1e-10;  // Solver.cpp:15
   constexpr double EPS = 1e-10;                   // pybindings.cpp:82 default epsilon
@@ -59,9 +65,9 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
   const bool even = !(lane & 1);
 
   double* wsm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * BwdQcqpSmem<T>::per_warp_doubles;
-  double* Lbuf = wsm;                             // [G][T][T]
-  double* Dbuf = Lbuf + 32 * T;                   // [G][T][T]   D rows, later A22 rows
-  double* Wbuf = Dbuf + 32 * T;                   // [32][WS]    L21 rows
+  double* Lbuf = wsm;                             // [G][T][S]
+  double* Dbuf = Lbuf + 32 * S;                   // [G][T][S]   D rows, later A22 rows
+  double* Wbuf = Dbuf + 32 * S;                   // [32][WS]    L21 rows
   double* vbuf = Wbuf + ((32 * WS + 1) & ~1);     // [32]
   double* dinvb = vbuf + 32;                      // [32]
   double* cbuf = dinvb + 32;                      // [4][32]     per-contact broadcast (indexed tile_base/2 + contact)
@@ -75,8 +81,8 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     const long long prob = p0 + tp;
     const bool vprob = prob < p.B;
     const bool valid = vprob && ti < N;
-    double* Lb = Lbuf + tp * T * T;
-    double* Db = Dbuf + tp * T * T;
+    double* Lb = Lbuf + tp * T * S;
+    double* Db = Dbuf + tp * T * S;
     double* Wb = Wbuf + tile_base * WS;
     double* vb = vbuf + tile_base;
     double* db = dinvb + tile_base;
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     for (int j = 0; j < R; j++)
       if (j == ti) drow[j] = 2 * gamma + drow[j];  // D_tild = D_tild + P  :656
 #pragma unroll
-    for (int j = 0; j < R; j++) Db[ti * T + j] = drow[j];
+    for (int j = 0; j < R; j += 2) *reinterpret_cast<double2*>(Db + ti * S + j) = make_double2(drow[j], drow[j + 1]);
     if (even) {
       cb0[c] = act ? slack : 0.0;
       cb1[c] = act ? bt0 : 0.0;
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       if (j < N) {
 #pragma unroll
         for (int k = 0; k < R; k += 2) {
-          double2 m = *reinterpret_cast<const double2*>(Db + j * T + k);
+          double2 m = *reinterpret_cast<const double2*>(Db + j * S + k);
           acc = fma(drow[k], m.x, acc);
           acc = fma(drow[k + 1], m.y, acc);
         }
@@ -282,7 +288,8 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     }
     __syncwarp();  // all lanes finished reading Db (D rows) and wrote Wb
 #pragma unroll
-    for (int j = 0; j < R; j++) Db[ti * T + j] = valid ? a22[j] : 0.0;  // Db now holds A22 (symmetric)
+    for (int j = 0; j < R; j += 2)  // Db now holds A22 (symmetric)
+      *reinterpret_cast<double2*>(Db + ti * S + j) = valid ? make_double2(a22[j], a22[j + 1]) : make_double2(0.0, 0.0);
     // Schur complement row: sc(ti,j) = A22(ti,j) - sum_c L21(ti,c) L21(j,c)
     double scinv[R];
     {
@@ -297,7 +304,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
         a[j] = (valid && j <= ti) ? (a22[j] - acc) : 0.0;
       }
       __syncwarp();
-      tile_spd_inverse<T, R>(a, scinv, Lb, db, N, ti, tile_base);
+      tile_spd_inverse<T, R, S>(a, scinv, Lb, db, N, ti, tile_base);
     }
 
     // ---- block solve  [b1; b2] = AA^-1 [t1; t2]   (t1, b1 per contact on the lane pair; t2, b2 per lane)
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       double acc2 = 0.0, acc3 = 0.0;
       for (int i = 0; i < N; i++) {
         const double xv = vb[i];
-        acc2 = fma(Db[i * T + ti], xv, acc2);  // A22 x2 (A22 symmetric: column read, conflict-free)
+        acc2 = fma(Db[i * S + ti], xv, acc2);  // A22 x2 (A22 symmetric: column read, conflict-free)
         acc3 = fma(Wb[i * WS + c], xv, acc3);  // L21^T x2
       }
       __syncwarp();

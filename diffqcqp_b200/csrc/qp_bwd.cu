@@ -21,11 +21,15 @@
 
 namespace dq {
 
+#ifndef DQ_BWD_PAD
+#define DQ_BWD_PAD 2  // padding of the [T][T] scratch rows, doubles (0: the round-1 layout, for A/B builds)
+#endif
 template <int T>
 struct BwdQpCfg {
   static constexpr int WARPS = (T == 32) ? 2 : 4;  // warps per CTA (independent; no CTA-level barrier)
-  // per warp: Cholesky scratch 32*T, masked-P rows 32*T, gemv operand 32, reciprocal pivots 32, x broadcast 32
-  static constexpr int per_warp_doubles = 2 * 32 * T + 3 * 32;
+  static constexpr int S = T + DQ_BWD_PAD;  // row stride of the two [T][T] scratch matrices (bank spread: see tile_spd_inverse)
+  // per warp: Cholesky scratch 32*S, masked-P rows 32*S, gemv operand 32, reciprocal pivots 32, x broadcast 32
+  static constexpr int per_warp_doubles = 2 * 32 * S + 3 * 32;
   static constexpr size_t bytes = (size_t)WARPS * per_warp_doubles * sizeof(double);
 };
 
@@ -68,11 +72,12 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
   const bool valid = vprob && ti < N;
 
   double* wsm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * BwdQpCfg<T>::per_warp_doubles;
-  double* Lb = wsm + tp * T * T;               // [T][T] Cholesky factor of this tile
-  double* Mb = wsm + 32 * T + tp * T * T;      // [T][T] masked P rows
-  double* vb = wsm + 64 * T + tile_base;       // [T] gemv operand
-  double* db = wsm + 64 * T + 32 + tile_base;  // [T] reciprocal pivots
-  double* xb = wsm + 64 * T + 64 + tile_base;  // [T] x broadcast for the outer product
+  constexpr int S = BwdQpCfg<T>::S;
+  double* Lb = wsm + tp * T * S;               // [T][S] Cholesky factor of this tile
+  double* Mb = wsm + 32 * S + tp * T * S;      // [T][S] masked P rows
+  double* vb = wsm + 64 * S + tile_base;       // [T] gemv operand
+  double* db = wsm + 64 * S + 32 + tile_base;  // [T] reciprocal pivots
+  double* xb = wsm + 64 * S + 64 + tile_base;  // [T] x broadcast for the outer product
 
   // ---- inputs straight into registers.  When the forward handed over diag(P) (p.state: a number for a problem it
   // found diagonal, NaN otherwise) and every problem of this group is diagonal, P is not read at all: 8N^2 of the
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
 #pragma unroll
     for (int j = 0; j < R; j++) pm[j] = (fr && ((fmask >> j) & 1u)) ? prow[j] : 0.0;
 #pragma unroll
-    for (int j = 0; j < R; j++) Mb[ti * T + j] = pm[j];
+    for (int j = 0; j < R; j += 2) *reinterpret_cast<double2*>(Mb + ti * S + j) = make_double2(pm[j], pm[j + 1]);
     __syncwarp();
     // AA(i,j) = sum_k Pm(i,k) Pm(j,k)   (P_ff P_ff^T; zero rows/cols for active indices)
 #pragma unroll
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
       if (j < N) {
 #pragma unroll
         for (int k = 0; k < R; k += 2) {
-          const double2 m = *reinterpret_cast<const double2*>(Mb + j * T + k);
+          const double2 m = *reinterpret_cast<const double2*>(Mb + j * S + k);
           acc = fma(pm[k], m.x, acc);
           acc = fma(pm[k + 1], m.y, acc);
         }
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
     double a[R], ainv[R];
 #pragma unroll
     for (int j = 0; j < R; j++) a[j] = (valid && j <= ti) ? aa[j] : 0.0;
-    tile_spd_inverse<T, R>(a, ainv, Lb, db, N, ti, tile_base);
+    tile_spd_inverse<T, R, S>(a, ainv, Lb, db, N, ti, tile_base);
     vb[ti] = valid ? abv : 0.0;
     __syncwarp();
     const double w = tile_row_dot<R>(ainv, vb, N);  // AA_tild_inv * Ab  :27
