@@ -216,17 +216,14 @@ __global__ void __launch_bounds__(BwdBoxSmem<T>::WARPS * 32) boxqp_bwd_kernel(co
           accw = fma(prow[k + 1] * w.y, m.y, accw);
         }
       }
-      if (j == ti) acc += nact + MU_IR;
+      acc = sel(j == ti, acc + (nact + MU_IR), acc);
       a22[j] = acc;
       a[j] = (valid && j <= ti) ? (acc - accw) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < R; j++) Db[ti * T + j] = valid ? a22[j] : 0.0;
-    if (!valid) {
 #pragma unroll
-      for (int j = 0; j < R; j++)
-        if (j == ti) a[j] = 1.0;  // padded lanes: identity (never read: tile_spd_inverse stops at N)
-    }
+    for (int j = 0; j < R; j++) a[j] = sel(!valid && j == ti, 1.0, a[j]);  // padded lanes: identity (never read: tile_spd_inverse stops at N)
     __syncwarp();
     tile_spd_inverse<T, R>(a, scinv, Lb, db, N, ti, tile_base);
   }

@@ -22,11 +22,21 @@ __device__ __forceinline__ double tile_sum(double v) {
   return v;
 }
 
+// c ? v : x on the bit patterns, so that what reaches the optimiser is a select and never a branch.  A chain of
+// `if (j == ti) x[j] = ...` over an unrolled loop (the per-lane "my diagonal entry" update) can be folded by nvcc 12.9
+// into a switch on ti and lowered to per-lane indexed jumps (BRX, every lane its own path): seen in the R = 24 backward
+// instances and, inside the refactorisation, as a 60x slowdown of the N = 24 forward (tests/test_abi.py guards it).
+__device__ __forceinline__ double sel(bool c, double v, double x) {
+  const long long m = -(long long)c;
+  return __longlong_as_double((__double_as_longlong(v) & m) | (__double_as_longlong(x) & ~m));
+}
+
 // ---------------------------------------------------------------- in-tile SPD inverse
 // Mirrors the reference's `chol = M.llt(); Minv.setIdentity(); chol.solveInPlace(Minv)`
 // (Solver.cpp:76-77, :22-23): Cholesky factor, then forward and backward substitution against the
 // identity.  Lane i enters with a[0..i] = lower-triangular part of row i of M (a[i] = diagonal) and
-// leaves with out[0..T) = row i of M^{-1} (= column i, M^{-1} is symmetric).
+// leaves with out[0..T) = row i of M^{-1} (= column i, M^{-1} is symmetric).  a[j] for j > i may hold anything
+// finite or not: what a lane computes for a column right of its diagonal is neither stored nor shuffled out.
 //
 // Lb   : this tile's T-row shared scratch, row stride S doubles (S >= T, even).  Entries with an index >= N must be
 //        zero on entry and are never written, so padded lanes/columns drop out of every sum.  S = T makes the

@@ -243,8 +243,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
       }
     } else {
 #pragma unroll
-    for (int j = 0; j < R; j++)
-      if (j == ti) drow[j] = 2 * gamma + drow[j];  // D_tild = D_tild + P  :656
+    for (int j = 0; j < R; j++) drow[j] = sel(j == ti, 2 * gamma + drow[j], drow[j]);  // D_tild = D_tild + P  :656
 #pragma unroll
     for (int j = 0; j < R; j += 2) *reinterpret_cast<double2*>(Db + ti * S + j) = make_double2(drow[j], drow[j + 1]);
     if (even) {
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
 #pragma unroll
     for (int j = 0; j < R; j++) {
       if (act && (j >> 1) == c) a22[j] += (2 * li) * ((j == ti) ? (2 * li) : (2 * lo));
-      if (j == ti) a22[j] += MU_IR;
+      a22[j] = sel(j == ti, a22[j] + MU_IR, a22[j]);
     }
     __syncwarp();  // all lanes finished reading Db (D rows) and wrote Wb
 #pragma unroll

@@ -177,8 +177,7 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
     __syncwarp();
     // diagonal: active rows hold l_i^2, everyone gets + mu_ir
 #pragma unroll
-    for (int j = 0; j < R; j++)
-      if (j == ti) aa[j] = (act ? xi * xi : aa[j]) + MU_IR;
+    for (int j = 0; j < R; j++) aa[j] = sel(j == ti, (act ? xi * xi : aa[j]) + MU_IR, aa[j]);
     double a[R], ainv[R];
 #pragma unroll
     for (int j = 0; j < R; j++) a[j] = (valid && j <= ti) ? aa[j] : 0.0;

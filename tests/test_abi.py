@@ -141,6 +141,26 @@ def test_algorithmic_bytes_match_survey():
     assert wl.qp_bytes(32) == 26368 - 256
 
 
+def test_sass_has_no_per_lane_indexed_jumps():
+    """No kernel contains an indexed jump (BRX / JMX).  nvcc 12.9 can fold an unrolled `if (j == lane_index) x[j] = ...`
+    chain into a switch lowered to per-lane jump tables: every lane of the warp then runs its own path (measured: the
+    N = 24 forward 60x slower with one such chain in the refactorisation).  common.cuh's sel() keeps those updates selects."""
+    import shutil
+    import subprocess
+    from diffqcqp_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    fn, bad = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split(":")[1].strip()
+        elif " BRX " in line or " JMX " in line:
+            bad[fn] = bad.get(fn, 0) + 1
+    assert not bad, bad
+
+
 def test_sass_of_the_persistent_forward_hot_loop():
     """Regression guard for the headline kernel (admm_fwd_diag8_kernel<PROX_NONNEG>): the code object holds it, it fits 72
     registers, its ADMM loops carry no divergence guards (BRA.DIV: the warp index is read through a shuffle so that
