@@ -30,9 +30,9 @@ size_t fwd_smem_bytes(int T) { return fwd_smem_bytes_impl(T); }
 #define DQ_FWD_WPS24 16  // resident warps per SM the 32-lane, 24-entry instance is sized for
 #endif
 #ifndef DQ_FWD_WPS16
-#define DQ_FWD_WPS16 16  // resident warps per SM the 16-lane instance is sized for
+#define DQ_FWD_WPS16 20  // resident warps per SM the 16-lane instance is sized for (96 registers; 16 -> 20: -2.3 % on the N = 16 QCQP forward, 24 and 32 spill and lose)
 #endif
-template <int T, int PROX, int R>
+template <int T, int PROX, int R, bool FULL>
 __global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : ((T == 32 && R == 24) ? DQ_FWD_WPS24 : (T == 16 ? DQ_FWD_WPS16 : 16))) / FWD_WARPS)
     admm_fwd_kernel(const FwdParams p) {
   constexpr int G = 32 / T;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : ((T == 32 && R 
   const long long g = (long long)blockIdx.x * FWD_WARPS + warp;  // this warp's group
   if (g >= p.n_groups) return;
   double* wsm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * FwdSmem<T>::per_warp_doubles;
-  solve_group<T, PROX, R>(p, g * G, p.B, lane, wsm);
+  solve_group<T, PROX, R, FULL>(p, g * G, p.B, lane, wsm);
 }
 
 
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(DIAG_WARPS * 32, (PROX == PROX_NONNEG ? DQ_DIA
         if (lane == 0) g = atomicAdd(&ctl[0], 1);
         g = __shfl_sync(FULL_MASK, g, 0);
         if (4 * g >= nb) break;
-        solve_group<8, PROX>(p, b0 + 4 * g, b0 + nb, lane, recs + w0 * R::D);
+        solve_group<8, PROX, 8, true>(p, b0 + 4 * g, b0 + nb, lane, recs + w0 * R::D);  // N == 8 here
         __syncwarp();
       }
       __syncthreads();
@@ -457,7 +457,8 @@ static cudaError_t launch_fwd_t(const FwdParams& p, cudaStream_t stream) {
   static_assert(FwdSmem<T>::bytes <= 48 * 1024, "forward scratch must fit the default dynamic shared memory limit");
   const long long grid = (p.n_groups + FWD_WARPS - 1) / FWD_WARPS;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  admm_fwd_kernel<T, PROX, R><<<(unsigned)grid, FWD_WARPS * 32, FwdSmem<T>::bytes, stream>>>(p);
+  if (p.N == R) admm_fwd_kernel<T, PROX, R, true><<<(unsigned)grid, FWD_WARPS * 32, FwdSmem<T>::bytes, stream>>>(p);  // N compiled in
+  else admm_fwd_kernel<T, PROX, R, false><<<(unsigned)grid, FWD_WARPS * 32, FwdSmem<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 

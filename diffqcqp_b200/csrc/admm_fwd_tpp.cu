@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(TPP_BLOCK, TppGeo<E>::CTAS) admm_fwd_tpp8_kern
       if (lane == 0) g = atomicAdd(&ctl[0], 1);
       g = __shfl_sync(FULL_MASK, g, 0);
       if (4 * g >= nb) break;
-      solve_group<8, PROX>(p, b0 + 4 * g, b0 + nb, lane, recs + warp * FwdSmem<8>::per_warp_doubles);
+      solve_group<8, PROX, 8, true>(p, b0 + 4 * g, b0 + nb, lane, recs + warp * FwdSmem<8>::per_warp_doubles);  // N == 8 here
       __syncwarp();
     }
     if (blockIdx.x == 0 && tid == 0 && p.dense_hint != nullptr) *(volatile int*)(p.dense_hint + 1) = 1;  // this launch has run

@@ -55,13 +55,15 @@ __device__ __forceinline__ double sel(bool c, double v, double x) {
 // R <= T is the row capacity the loops are unrolled to (N <= R): a 32-lane tile with N <= 24 runs the R = 24 instance,
 // 44 % fewer unrolled triangular-loop instructions and 16 fewer registers per array (the T = 32 forward is
 // instruction-fetch bound, profiles/r01_qcqp_n24_ncu_lines.txt: no_inst 37 % of the stall samples).
-template <int T, int R = T, int S = T>
+// FULL = the caller knows N == R: the per-column / per-row `< N` tests (uniform branches around each unrolled block) go
+// away and the whole inverse is straight-line code.
+template <int T, int R = T, int S = T, bool FULL = false>
 __device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R], double* Lb, double* dinv,
                                                  int N, int ti, int tile_base_lane) {
   // ---- Cholesky, left-looking, one column per step (Eigen LLT unblocked order)
 #pragma unroll
   for (int k = 0; k < R; k++) {
-    if (k < N) {
+    if (FULL || k < N) {
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
       for (int j = 0; j + 1 < k; j += 2) {
@@ -74,7 +76,7 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R
       const double rp = rsqrt(skk);                        // 1 / L(k,k)
       const double val = (ti == k) ? skk * rp : s * rp;    // L(k,k) = sqrt(pivot);  L(i,k) = s / L(k,k)
       a[k] = val;
-      if (ti >= k && ti < N) {
+      if (ti >= k && ((FULL && R == T) || ti < N)) {
         Lb[ti * S + k] = val;
         Lb[k * S + ti] = val;
       }
@@ -85,7 +87,7 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R
   // ---- forward substitution L y = e_ti
 #pragma unroll
   for (int i = 0; i < R; i++) {
-    if (i < N) {
+    if (FULL || i < N) {
       double acc0 = (i == ti) ? 1.0 : 0.0, acc1 = 0.0;
 #pragma unroll
       for (int j = 0; j + 1 < i; j += 2) {
@@ -101,7 +103,7 @@ __device__ __forceinline__ void tile_spd_inverse(double (&a)[R], double (&out)[R
   // ---- back substitution L^T x = y   (L^T(i,j) = L(j,i) = Lb[i][j] for j > i)
 #pragma unroll
   for (int i = R - 1; i >= 0; i--) {
-    if (i < N) {
+    if (FULL || i < N) {
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
       for (int j = i + 1; j + 1 < R; j += 2) {

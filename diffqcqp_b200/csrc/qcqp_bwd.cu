@@ -38,10 +38,14 @@ struct BwdQcqpSmem {
 #ifndef DQ_QCQP_BWD_MINB32
 #define DQ_QCQP_BWD_MINB32 4
 #endif
+#ifndef DQ_QCQP_BWD_MINB16
+#define DQ_QCQP_BWD_MINB16 6
+#endif
 // R = row capacity (N <= R <= T): register arrays and unrolled loops stop at R; a 32-lane tile with N <= 24 runs R = 24
 // (fewer registers, a third less unrolled code; results are the same bits, the skipped terms are exact zeros).
-template <int T, int R>
-__global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP_BWD_MINB32 : (T == 16 ? 6 : 4)))
+// FULL = launched with p.N == R: N is a compile-time constant (every `< N` test around an unrolled block folds away).
+template <int T, int R, bool FULL>
+__global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP_BWD_MINB32 : (T == 16 ? DQ_QCQP_BWD_MINB16 : 4)))
     qcqp_bwd_kernel(const BwdParams p) {
   constexpr int G = 32 / T;
   constexpr int T2 = T / 2;
@@ -52,7 +56,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
   constexpr double MU_IR = 1e-7, EPS_IR = 1e-10;  // Solver.cpp:15
   constexpr double EPS = 1e-10;                   // pybindings.cpp:82 default epsilon
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int N = p.N;
+  const int N = FULL ? R : p.N;
   const int nc = N / 2;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
         a[j] = (valid && j <= ti) ? (a22[j] - acc) : 0.0;
       }
       __syncwarp();
-      tile_spd_inverse<T, R, S>(a, scinv, Lb, db, N, ti, tile_base);
+      tile_spd_inverse<T, R, S, FULL>(a, scinv, Lb, db, N, ti, tile_base);
     }
 
     // ---- block solve  [b1; b2] = AA^-1 [t1; t2]   (t1, b1 per contact on the lane pair; t2, b2 per lane)
@@ -407,7 +411,8 @@ static cudaError_t launch_qcqp_bwd_t(const BwdParams& p, cudaStream_t stream) {
   constexpr int WARPS = BwdQcqpSmem<T>::WARPS;
   const long long grid = (p.n_groups + WARPS - 1) / WARPS;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  qcqp_bwd_kernel<T, R><<<(unsigned)grid, WARPS * 32, BwdQcqpSmem<T>::bytes, stream>>>(p);
+  if (p.N == R) qcqp_bwd_kernel<T, R, true><<<(unsigned)grid, WARPS * 32, BwdQcqpSmem<T>::bytes, stream>>>(p);
+  else qcqp_bwd_kernel<T, R, false><<<(unsigned)grid, WARPS * 32, BwdQcqpSmem<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 

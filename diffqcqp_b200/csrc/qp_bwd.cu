@@ -52,14 +52,15 @@ __device__ __forceinline__ void load_row_bwd(double (&row)[T], const double* __r
 }
 
 // R = row capacity (N <= R <= T): register arrays and unrolled loops stop at R (a 32-lane tile with N <= 24 runs R = 24).
-template <int T, int R>
+// FULL = launched with p.N == R: N is a compile-time constant (every `< N` test around an unrolled block folds away).
+template <int T, int R, bool FULL>
 __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 16 ? 4 : 6))) qp_bwd_kernel(const BwdParams p) {
   constexpr int G = 32 / T;
   constexpr int WARPS = BwdQpCfg<T>::WARPS;
   constexpr double MU_IR = 1e-7, EPS_IR = 1e-10;  // iterative_refinement defaults, Solver.cpp:15
   constexpr double EPS_ACT = 1e-10;               // pybindings.cpp:80 default, Solver.cpp:129,:140
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int N = p.N;
+  const int N = FULL ? R : p.N;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long g = (long long)blockIdx.x * WARPS + warp;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
     double a[R], ainv[R];
 #pragma unroll
     for (int j = 0; j < R; j++) a[j] = (valid && j <= ti) ? aa[j] : 0.0;
-    tile_spd_inverse<T, R, S>(a, ainv, Lb, db, N, ti, tile_base);
+    tile_spd_inverse<T, R, S, FULL>(a, ainv, Lb, db, N, ti, tile_base);
     vb[ti] = valid ? abv : 0.0;
     __syncwarp();
     const double w = tile_row_dot<R>(ainv, vb, N);  // AA_tild_inv * Ab  :27
@@ -239,7 +240,8 @@ static cudaError_t launch_qp_bwd_t(const BwdParams& p, cudaStream_t stream) {
   constexpr int WARPS = BwdQpCfg<T>::WARPS;
   const long long grid = (p.n_groups + WARPS - 1) / WARPS;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  qp_bwd_kernel<T, R><<<(unsigned)grid, WARPS * 32, BwdQpCfg<T>::bytes, stream>>>(p);
+  if (p.N == R) qp_bwd_kernel<T, R, true><<<(unsigned)grid, WARPS * 32, BwdQpCfg<T>::bytes, stream>>>(p);
+  else qp_bwd_kernel<T, R, false><<<(unsigned)grid, WARPS * 32, BwdQpCfg<T>::bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
