@@ -29,11 +29,17 @@ size_t fwd_smem_bytes(int T) { return fwd_smem_bytes_impl(T); }
 #ifndef DQ_FWD_WPS24
 #define DQ_FWD_WPS24 16  // resident warps per SM the 32-lane, 24-entry instance is sized for
 #endif
+#ifndef DQ_FWD_WPS8
+#define DQ_FWD_WPS8 28  // resident warps per SM the 8-lane instance is sized for (72 registers; 32 -> 28: -2..4 % on the dense N = 8 forwards, 24 and 20 lose)
+#endif
+#ifndef DQ_FWD_WPS32
+#define DQ_FWD_WPS32 16  // resident warps per SM the 32-lane, 32-entry instance is sized for
+#endif
 #ifndef DQ_FWD_WPS16
 #define DQ_FWD_WPS16 20  // resident warps per SM the 16-lane instance is sized for (96 registers; 16 -> 20: -2.3 % on the N = 16 QCQP forward, 24 and 32 spill and lose)
 #endif
 template <int T, int PROX, int R, bool FULL>
-__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? 32 : ((T == 32 && R == 24) ? DQ_FWD_WPS24 : (T == 16 ? DQ_FWD_WPS16 : 16))) / FWD_WARPS)
+__global__ void __launch_bounds__(FWD_WARPS * 32, (T == 8 ? DQ_FWD_WPS8 : ((T == 32 && R == 24) ? DQ_FWD_WPS24 : (T == 16 ? DQ_FWD_WPS16 : DQ_FWD_WPS32))) / FWD_WARPS)
     admm_fwd_kernel(const FwdParams p) {
   constexpr int G = 32 / T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
