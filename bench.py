@@ -502,6 +502,33 @@ def run_cfg5(L, dev, rank, world, barrier, steps=6, scatter_steps=3):
     scatter_ms = timed(scatter_step, scatter_steps)
     sc_only = torch.tensor([t_sc[0] / scatter_steps], dtype=torch.float64, device=dev)
     dist.all_reduce(sc_only, op=dist.ReduceOp.MAX)
+    # the same, software-pipelined: every rank's shard in PIPE_CHUNKS pieces, piece c solved while piece c+1 is on the wire
+    # and piece c-1's results travel back (shard.solve_sharded_pipelined)
+    PIPE_CHUNKS = 4
+
+    def pipe_fn(P, q, l_n, mu, g, lo, hi):
+        n, sp = hi - lo, stream.cuda_stream
+        o = {k: d[k][lo:hi] for k in ("x", "st", "gP", "gq", "gl", "gm")}
+        if n:
+            _lib.check(L.dq_qcqp_forward_ex(P.data_ptr(), q.data_ptr(), l_n.data_ptr(), mu.data_ptr(), None, o["x"].data_ptr(), None,
+                                            o["st"].data_ptr(), n, N5, EPS, MU_PROX, MAX_ITER, 1, sp), "forward")
+            _lib.check(L.dq_qcqp_backward_ex2(P.data_ptr(), q.data_ptr(), l_n.data_ptr(), mu.data_ptr(), o["x"].data_ptr(), g.data_ptr(),
+                                              o["st"].data_ptr(), o["gP"].data_ptr(), o["gq"].data_ptr(), o["gl"].data_ptr(),
+                                              o["gm"].data_ptr(), None, None, n, N5, sp), "backward")
+        return o["x"], o["gq"]
+
+    def pipe_step(_k):
+        shard.solve_sharded_pipelined(pipe_fn, full, B5 * world, chunks=PIPE_CHUNKS, src=0, device=dev, trailing=trailing)
+        torch.cuda.synchronize(dev)
+
+    pipe_step(0)
+    pipe_ms = timed(pipe_step, scatter_steps)
+    sweep = {}
+    for c in [int(v) for v in os.environ.get("DQ_CFG5_CHUNKS", "").split(",") if v]:  # experiment hook (scripts/cfg5_pipe.py)
+        PIPE_CHUNKS_SAVED, PIPE_CHUNKS = PIPE_CHUNKS, c
+        pipe_step(0)
+        sweep[str(c)] = timed(pipe_step, scatter_steps)
+        PIPE_CHUNKS = PIPE_CHUNKS_SAVED
     egress = sum(int(f.numel()) * 8 for f in full) * (world - 1) // world if rank == 0 else 0
     eg = torch.tensor([float(egress)], dtype=torch.float64, device=dev)
     dist.all_reduce(eg, op=dist.ReduceOp.MAX)
@@ -515,13 +542,16 @@ def run_cfg5(L, dev, rank, world, barrier, steps=6, scatter_steps=3):
                               "step_frac_hbm": (fb + bb) * B5 / (resident_ms * 1e-3) / 1e9 / peak},
            "scatter_inclusive": {"ms_per_step": scatter_ms, "value": B5 * world / (scatter_ms * 1e-3), "unit": "solves/s",
                                  "scatter_ms": float(sc_only.item())},
+           "scatter_pipelined": {"ms_per_step": pipe_ms, "value": B5 * world / (pipe_ms * 1e-3), "unit": "solves/s", "chunks": PIPE_CHUNKS,
+                                 "api": "diffqcqp_b200.shard.solve_sharded_pipelined", **({"sweep_ms": sweep} if sweep else {})},
            "root_egress_bytes": egress,
            "nccl_gbs": egress / (float(sc_only.item()) * 1e-3) / 1e9 if sc_only.item() > 0 else None,
            "nccl_reference_gbs": {"nvlink5_nominal_per_direction": 900.0, "measured_peer_copy_per_direction": 770.0},
            "note": "scatter = grouped NCCL send/recv (ncclGroup of isend/irecv, diffqcqp_b200/shard.py) of (P, q, l_n, mu, grad_l) from "
                    "rank 0; gather of x* and grad_q (grad_P stays sharded).  Every byte bound for another rank leaves rank 0 exactly "
                    "once, so its egress -- (world-1)/world of the batch -- is the floor for any scatter schedule (a tree moves the "
-                   "same bytes out of the root); the achieved rate against the 900 GB/s per direction of its NVLink ports is nccl_gbs."}
+                   "same bytes out of the root); the achieved rate against the 900 GB/s per direction of its NVLink ports is nccl_gbs.  "
+                   "scatter_pipelined overlaps that egress with the solves (pieces of the shard), the same bytes and results."}
     del sets, full
     torch.cuda.empty_cache()
     return out
@@ -553,6 +583,9 @@ def run_b200_arm(args):
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's kernels on a high-priority stream: in cfg5's pipelined scatter the root's send kernels then get SM slots ahead of
+        # the solve's CTAs queued behind them (8 x B200: 11.8 -> 9.3 ms per step; nothing else in this file overlaps NCCL with compute)
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     kind, B, N, kw, desc = WORKLOADS[args.workload]

@@ -63,3 +63,45 @@ def test_scatter_solve_gather_world2(tmp_path, B):
     mp.spawn(_worker, args=(2, port, B, 8, str(tmp_path)), nprocs=2, join=True)
     err, n = np.load(tmp_path / "ok.npy")
     assert n == B and err == 0.0  # sharding must not change any bit of any problem's result
+
+
+def _worker_pipelined(rank, world, port, B, N, chunks, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as orc  # the CPU checker stands in for the per-rank solve (tests only)
+        from diffqcqp_b200 import workloads as wl
+        P = q = None
+        if rank == 0:
+            P, q, _ = wl.qp_dense(B, N, seed=4)
+        seen = []
+
+        def local_solve(Pl, ql, lo, hi):
+            assert Pl.shape[0] == hi - lo
+            seen.append((lo, hi))
+            x = torch.from_numpy(orc.qp_forward(Pl.numpy(), ql.numpy(), None, 1e-7, 1000)) if hi > lo else torch.empty((0, N, 1), dtype=torch.float64)
+            return x, 2.0 * x[:, :1]          # two outputs with different trailing shapes
+
+        outs = shard.solve_sharded_pipelined(local_solve, [P, q] if rank == 0 else None, B, chunks=chunks, src=0,
+                                             device=torch.device("cpu"), trailing=[(N, N), (N, 1)])
+        n_loc = shard.shard_sizes(B, world)[rank]
+        assert len(seen) == chunks and seen[0][0] == 0 and seen[-1][1] == n_loc
+        assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+        if rank == 0:
+            ref = orc.qp_forward(P.numpy(), q.numpy(), None, 1e-7, 1000)
+            np.save(os.path.join(out_dir, "okp.npy"), np.array([float(np.abs(outs[0].numpy() - ref).max()),
+                                                                 float(np.abs(outs[1].numpy() - 2.0 * ref[:, :1]).max()), outs[0].shape[0]]))
+        else:
+            assert outs is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,chunks", [(37, 3), (10, 4), (5, 4)])
+def test_pipelined_scatter_solve_gather_world2(tmp_path, B, chunks):
+    """Ragged shards, ragged pieces (and empty pieces when a shard has fewer problems than pieces): same bits as one solve."""
+    port = _free_port()
+    mp.spawn(_worker_pipelined, args=(2, port, B, 8, chunks, str(tmp_path)), nprocs=2, join=True)
+    e0, e1, n = np.load(tmp_path / "okp.npy")
+    assert n == B and e0 == 0.0 and e1 == 0.0
