@@ -31,6 +31,17 @@ __device__ __forceinline__ double sel(bool c, double v, double x) {
   return __longlong_as_double((__double_as_longlong(v) & m) | (__double_as_longlong(x) & ~m));
 }
 
+// Number of non-zero entries of a register row.  "Does my row have an off-diagonal non-zero?" is asked as
+// row_nnz(row) > (diagonal != 0) with the diagonal loaded on its own: the direct form -- an unrolled
+// `if (j == ti) d = row[j]; else nz |= row[j] != 0` -- compiles to ~8 instructions per entry (nested predicate selects).
+template <int R>
+__device__ __forceinline__ int row_nnz(const double (&row)[R]) {
+  int n = 0;
+#pragma unroll
+  for (int j = 0; j < R; j++) n += (row[j] != 0.0) ? 1 : 0;
+  return n;
+}
+
 // ---------------------------------------------------------------- in-tile SPD inverse
 // Mirrors the reference's `chol = M.llt(); Minv.setIdentity(); chol.solveInPlace(Minv)`
 // (Solver.cpp:76-77, :22-23): Cholesky factor, then forward and backward substitution against the

@@ -132,13 +132,8 @@ __global__ void __launch_bounds__(BwdQcqpSmem<T>::WARPS * 32, (T == 32 ? DQ_QCQP
     }
 
     // is every problem of this group diagonal?  (decided from the data, warp-uniform)
-    double pd = 0.0;
-    bool nzoff = false;
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      if (j == ti) pd = drow[j];
-      else nzoff |= (drow[j] != 0.0);
-    }
+    const double pd = stashed ? sv : (valid ? __ldg(p.P + (prob * N + ti) * N + ti) : 0.0);  // = drow[ti] (row_nnz, common.cuh)
+    const bool nzoff = row_nnz<R>(drow) > (pd != 0.0 ? 1 : 0);
     const bool diagP = !__any_sync(FULL_MASK, nzoff);
 
     // ---- dualFromPrimalQCQP (Solver.cpp:584-617)

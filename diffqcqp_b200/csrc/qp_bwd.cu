@@ -98,12 +98,8 @@ __global__ void __launch_bounds__(BwdQpCfg<T>::WARPS * 32, (T == 8 ? 8 : (T == 1
     for (int j = 0; j < R; j++) prow[j] = 0.0;  // only the dense branch reads it
   } else {
     load_row_bwd<R>(prow, p.P + (prob * N + ti) * N, N, valid, vecP);
-    bool nz = false;
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      if (j == ti) pdiag = valid ? prow[j] : 1.0;
-      else nz |= (prow[j] != 0.0);
-    }
+    pdiag = valid ? __ldg(p.P + (prob * N + ti) * N + ti) : 1.0;  // = prow[ti] (row_nnz, common.cuh)
+    const bool nz = row_nnz<R>(prow) > ((valid && pdiag != 0.0) ? 1 : 0);
     dense = __any_sync(FULL_MASK, nz);  // warp-uniform
   }
 
