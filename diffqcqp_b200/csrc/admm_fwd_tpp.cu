@@ -149,35 +149,6 @@ __device__ __forceinline__ double sum_local(const double (&v)[E]) {
   else return __dadd_rn(v[0], v[1]);
 }
 
-// Branch-free sqrt / reciprocal: the fast paths of CUDA's own IEEE sqrt() and 1/x, instruction for instruction (MUFU seed,
-// Newton steps, final correction), without the range-check branch into the slow path -- so two or eight of them interleave
-// in one basic block.  Valid (and correctly rounded, i.e. bit-identical to sqrt() / 1.0/x: tests/test_parity_gpu.py,
-// dq_selftest_inverse) for arguments whose exponent is well inside the double range, which fast_ok() checks.
-__device__ __forceinline__ double fast_sqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H: high word only
-  const double y0 = __hiloint2double(__double2hiint(y), __double2hiint(x) - 0x03500000);  // the library's seed, low word included
-  const double e = __fma_rn(x, -__dmul_rn(y0, y0), 1.0);
-  const double t = __fma_rn(e, 0.375, 0.5);
-  const double y1 = __fma_rn(t, __dmul_rn(y0, e), y0);
-  const double g = __dmul_rn(x, y1);
-  const double h = __hiloint2double(__double2hiint(y1) - 0x100000, __double2loint(y1));  // y1 / 2
-  const double d = __fma_rn(g, -g, x);
-  return __fma_rn(d, h, g);
-}
-__device__ __forceinline__ double fast_rcp(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RCP64H: high word only
-  const double y0 = __hiloint2double(__double2hiint(y), __double2hiint(x) + 0x00300402);  // the library's seed, low word included
-  const double e = __fma_rn(-x, y0, 1.0);
-  const double y1 = __fma_rn(y0, __fma_rn(e, e, e), y0);
-  const double e3 = __fma_rn(-x, y1, 1.0);
-  return __fma_rn(y1, e3, y1);
-}
-__device__ __forceinline__ bool fast_ok(double x) {  // positive, finite, 2^-766 <= x < 2^769
-  return (unsigned)(__double2hiint(x) - 0x10100000) < 0x5ff00000u;
-}
-
 __device__ __forceinline__ unsigned long long abs_bits(double a) {
   return (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffULL;
 }
