@@ -181,6 +181,31 @@ def test_qcqp_forward_vs_oracle(dq, wl, oracle, B, N, eps, seed, diag):
     assert np.all(np.hypot(xn[:, 0::2], xn[:, 1::2]) <= r * (1 + 1e-12) + 1e-300)
 
 
+@pytest.mark.parametrize("N,k", [(16, 300), (16, -300), (24, 280), (8, -290)])
+def test_qcqp_forward_extreme_scale_vs_oracle(dq, wl, oracle, N, k):
+    """Dense QCQPs with P and q scaled by 2^k, |k| large enough that P^4 leaves the double range.  The kernels' power
+    iteration runs on P^4 after an exact power-of-two pre-scale (the reference normalises after every product,
+    Solver.cpp:50-54), so lambda_max and rho_0 must still come out right.  These inputs are degenerate for the reference
+    itself (absolute eps: the tiny problems stop after one iteration, the huge ones run into max_iter), which is exactly
+    what the kernels have to reproduce: same iteration counts, finite results, x within the usual bar for the tiny
+    problems and within 1e-6 relative for the 300-iteration unconverged ones."""
+    B = 96
+    P, q, l_n, mu, _ = wl.qcqp_dense(B, N, seed=500 + N)
+    s = 2.0 ** k
+    P, q = P * s, q * s
+    xo, ito = oracle.qcqp_forward(P.numpy(), q.numpy(), l_n.numpy(), mu.numpy(), None, EPS, 300, return_iters=True)
+    x, it = dq.qcqp_forward(*dev(P, q, l_n, mu), EPS, 300, return_iters=True)
+    xn = x.cpu().numpy()
+    assert np.all(np.isfinite(xn))
+    mism = int((it.cpu().numpy() != ito).sum())
+    err = float(np.abs(xn - xo).max() / max(np.abs(xo).max(), 1e-300))
+    report(f"extreme-scale qcqp N={N} scale 2^{k}: iteration-count mismatches {mism}/{B}, iterations mean {ito.mean():.1f}, max rel |x - x_oracle| {err:.2e}")
+    assert mism == 0
+    if k < 0:
+        check_x(x, xo, EPS)
+    assert err <= 1e-6
+
+
 @pytest.mark.parametrize("B,N,seed,diag", [(2048, 8, 30, False), (1024, 16, 31, False), (512, 24, 32, False),
                                             (300, 32, 33, False), (512, 16, 34, True), (100, 6, 35, False)])
 def test_qcqp_backward_vs_oracle(dq, wl, oracle, B, N, seed, diag):
